@@ -1,0 +1,26 @@
+"""CPU oracle for the kNN -> normals -> point-to-plane ICP path (TEST INFRASTRUCTURE ONLY).
+
+A C++17 restatement of the reference's CPU algorithm (see oracle.cpp for the per-function
+reference citations) loaded through ctypes.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this package; nothing
+under ``threecrate_b200/`` does.
+
+PARITY UNPINNED: the reference is Rust-only (no toolchain here) and holds no golden vectors
+for this path; the oracle is pinned by the reference's own inline test assertions and by
+independent numpy/scipy cross-checks (tests/test_oracle_*.py).
+"""
+from .oracle import (  # noqa: F401
+    IcpResult,
+    OracleKdTree,
+    brute_knn,
+    build,
+    estimate_normals,
+    icp_point_to_plane,
+    iso_apply,
+    iso_mul,
+    k_nearest_neighbors,
+    max_threads,
+    normals_f64,
+    solve6,
+    symmetric_eigen3,
+)
