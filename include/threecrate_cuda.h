@@ -1,0 +1,182 @@
+/* threecrate_cuda.h — C ABI of the B200-native kNN -> normals -> point-to-plane ICP path.
+ *
+ * This is the boundary the reference's Rust crates would bind (a `threecrate-cuda` crate behind a
+ * `cuda` cargo feature on threecrate-algorithms; see INTEGRATION.md for the `extern "C"` block and
+ * the #[cfg(feature = "cuda")] routing).  Plain pointers and sizes only; no torch/nalgebra types.
+ * Citations are paths relative to the reference checkout.
+ *
+ * Conventions
+ *   - Every function returns a tc_status; the message for the last failure on a context is
+ *     available from tc_last_error().  Status codes map 1:1 onto threecrate_core::Error variants
+ *     (threecrate-core/src/error.rs:7-28): InvalidData, Algorithm, Gpu.
+ *   - Points are AoS f32 triples, i.e. exactly `Vec<Point3f>::as_ptr()` (nalgebra Point3<f32> is a
+ *     repr(C) [f32;3]; threecrate-core/src/point.rs:8).  Normals output is AoS f32 sextuples ==
+ *     `#[repr(C)] NormalPoint3f {position, normal}` (threecrate-core/src/point.rs:31-36).
+ *   - Indices are u32 (the reference's own tree limits N < 2^32: NIL = u32::MAX,
+ *     threecrate-algorithms/src/nearest_neighbor.rs:8); TC_NO_INDEX pads short rows.
+ *   - Rigid transforms cross the ABI as 7 floats [tx,ty,tz, qi,qj,qk,qw] (nalgebra Isometry3
+ *     layout is not relied upon).
+ *   - A tc_context owns one CUDA stream on one device; calls on a context are serialised on that
+ *     stream; contexts are independent (one per thread, like rayon workers sharing `&KdTree`).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns TC_GPU.
+ *   - Tie rule for bit-equal squared distances: ascending (d2, original index) — the order of
+ *     SimdBruteForceSearch (threecrate-algorithms/src/simd_distance.rs:370-385,444-452).
+ */
+#ifndef THREECRATE_CUDA_H
+#define THREECRATE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_NO_INDEX 0xFFFFFFFFu
+
+typedef enum tc_status {
+  TC_OK = 0,
+  TC_INVALID_DATA = 1, /* Error::InvalidData */
+  TC_ALGORITHM = 2,    /* Error::Algorithm   */
+  TC_GPU = 3           /* Error::Gpu         */
+} tc_status;
+
+typedef struct tc_context tc_context; /* device + stream + scratch                       */
+typedef struct tc_cloud tc_cloud;     /* device-resident PointCloud<Point3f>              */
+typedef struct tc_index tc_index;     /* uniform-grid spatial index over a tc_cloud       */
+typedef struct tc_comm tc_comm;       /* NCCL communicator for the sharded ICP reduction  */
+
+/* ---- context -------------------------------------------------------------------------- */
+int tc_context_create(int device, tc_context** out);
+void tc_context_destroy(tc_context* ctx);
+const char* tc_last_error(const tc_context* ctx);
+/* cudaStream_t of the context (for CUDA-event timing by the caller). */
+void* tc_context_stream(tc_context* ctx);
+int tc_context_synchronize(tc_context* ctx);
+/* Number of kernels this library has launched on the context so far. */
+uint64_t tc_launch_count(const tc_context* ctx);
+/* CUDA-event timer on the context's stream: start, run calls, stop -> elapsed ms. */
+int tc_timer_start(tc_context* ctx);
+int tc_timer_stop(tc_context* ctx, float* ms_out);
+const char* tc_version(void);
+
+/* ---- device-resident cloud (replaces per-call re-pack/upload of the wgpu path) ------------ */
+/* Upload `n` points from host AoS f32 (PointCloud<Point3f>.points, point_cloud.rs:11-13). */
+int tc_cloud_upload(tc_context* ctx, const float* xyz_aos, uint64_t n, tc_cloud** out);
+/* Upload from strided host records, e.g. KITTI .bin x,y,z,intensity stride 16
+ * (threecrate-io/src/lidar.rs:310-345). */
+int tc_cloud_upload_strided(tc_context* ctx, const void* base, uint64_t n, uint32_t stride_bytes,
+                            tc_cloud** out);
+/* Wrap points that already live in device memory (copied; AoS f32, n x 3). */
+int tc_cloud_from_device(tc_context* ctx, const float* d_xyz_aos, uint64_t n, tc_cloud** out);
+void tc_cloud_free(tc_cloud* cloud);
+uint64_t tc_cloud_len(const tc_cloud* cloud);
+
+/* ---- spatial index (replaces KdTree::new, nearest_neighbor.rs:37-60) ---------------------- */
+/* Builds the uniform grid: bbox -> cell keys -> hand-written LSD radix sort -> cell-range scan ->
+ * sorted float4 (x,y,z,original index).  cell_size <= 0 selects it automatically from `k_hint`
+ * (the k the index will mostly be queried with; 1 for ICP correspondence search). */
+int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
+                   tc_index** out);
+void tc_index_free(tc_index* index);
+
+typedef struct tc_index_info {
+  uint64_t n_points;
+  uint64_t n_cells;
+  uint32_t dims[3];
+  float cell_size;
+  float bbox_min[3];
+  float bbox_max[3];
+  uint32_t occupied_cells;
+  uint32_t max_cell_population;
+} tc_index_info;
+int tc_index_get_info(const tc_index* index, tc_index_info* out);
+
+/* ---- kNN (KdTree::find_k_nearest nearest_neighbor.rs:177-251;
+ *           PointCloudNeighbors::k_nearest_neighbors point_cloud_ops.rs:80-105) ---------------
+ * queries_aos == NULL: the indexed cloud queries itself (nq must equal its length) and, with
+ * exclude_self != 0, each point's own index is removed (kNN(k+1), retain idx != i, truncate k).
+ * Outputs are HOST buffers: idx_out/dist_out are nq x k row-major (TC_NO_INDEX / +inf padded when
+ * fewer than k exist), dist_out = sqrt(d2) (may be NULL), count_out[nq] valid entries (may be
+ * NULL).  Rows ascend by (d2, index).  k == 0 or an empty cloud yields zero counts. */
+int tc_knn(tc_context* ctx, const tc_index* index, const float* queries_aos, uint64_t nq,
+           uint32_t k, int exclude_self, uint32_t* idx_out, float* dist_out, uint32_t* count_out);
+/* Same with DEVICE output buffers (results stay resident; no readback). */
+int tc_knn_device(tc_context* ctx, const tc_index* index, const float* d_queries_aos, uint64_t nq,
+                  uint32_t k, int exclude_self, uint32_t* d_idx_out, float* d_dist_out,
+                  uint32_t* d_count_out);
+/* KdTree::find_radius_neighbors (nearest_neighbor.rs:254-298) for one query: all points with
+ * d2 <= radius^2, ascending by distance; at most `capacity` written, total returned in n_found. */
+int tc_radius_search(tc_context* ctx, const tc_index* index, const float query[3], float radius,
+                     uint32_t* idx_out, float* dist_out, uint64_t capacity, uint64_t* n_found);
+
+/* ---- normals (estimate_normals_with_config, normals.rs:257-357) ---------------------------
+ * Drop-in: host AoS in, host AoS NormalPoint3f out (n x 6 f32).  Includes upload + index build,
+ * as the reference's call includes KdTree::new (normals.rs:272).
+ *   n == 0 -> TC_OK, nothing written (checked BEFORE k, normals.rs:261-269);
+ *   k < 3  -> TC_INVALID_DATA "k_neighbors must be at least 3";
+ *   radius < 0 means None; viewpoint == NULL means the bbox-derived default (normals.rs:275-303). */
+int tc_estimate_normals(tc_context* ctx, const float* xyz_aos, uint64_t n, uint32_t k, float radius,
+                        int consistent_orientation, const float* viewpoint3, float* out_aos);
+/* Same on a prebuilt index (host output). */
+int tc_estimate_normals_indexed(tc_context* ctx, const tc_index* index, uint32_t k, float radius,
+                                int consistent_orientation, const float* viewpoint3,
+                                float* out_aos);
+/* Device-resident output, optionally only for the shard [shard_begin, shard_end) of the index's
+ * spatially sorted order (multi-GPU: queries sharded over a replicated grid).  d_out_aos is the
+ * full n x 6 buffer indexed by ORIGINAL point index; only the shard's rows are written. */
+int tc_estimate_normals_device(tc_context* ctx, const tc_index* index, uint32_t k, float radius,
+                               int consistent_orientation, const float* viewpoint3,
+                               uint64_t shard_begin, uint64_t shard_end, float* d_out_aos);
+
+/* ---- point-to-plane ICP (icp_point_to_plane_detailed, registration.rs:508-602) ------------ */
+typedef struct tc_icp_result {
+  float transform[7]; /* tx,ty,tz, qi,qj,qk,qw                        (ICPResult.transformation) */
+  float mse;          /*                                              (ICPResult.mse)            */
+  uint32_t iterations;/*                                              (ICPResult.iterations)     */
+  int32_t converged;  /*                                              (ICPResult.converged)      */
+  uint64_t n_correspondences; /* pairs of the last executed iteration (ICPResult.correspondences) */
+} tc_icp_result;
+
+/* Drop-in: host buffers in, result out.  Includes target index build (registration.rs:536).
+ *   ns == 0 or nt == 0 -> TC_INVALID_DATA; n_normals != nt -> TC_INVALID_DATA;
+ *   max_iters == 0 -> TC_INVALID_DATA (registration.rs:517-531);
+ *   < 6 valid pairs -> TC_ALGORITHM; singular system -> TC_ALGORITHM (registration.rs:568-572,
+ *   432-438).  max_corr_dist < 0 means None.  pairs_out (may be NULL): capacity ns x 2 u64,
+ *   (source index, target index) of the last executed iteration in source order. */
+int tc_icp_point_to_plane(tc_context* ctx, const float* src_aos, uint64_t ns, const float* tgt_aos,
+                          uint64_t nt, const float* tgt_normals_aos, uint64_t n_normals,
+                          const float init[7], uint32_t max_iters, float max_corr_dist,
+                          float conv_threshold, tc_icp_result* out, uint64_t* pairs_out);
+
+/* Device-resident variant: source cloud, prebuilt target index and target normals (device AoS,
+ * nt x 3, original target order) stay in HBM; the whole iteration loop runs without a host
+ * round-trip.  With comm != NULL every rank passes ITS source shard and the per-iteration
+ * 29-scalar normal-equation sums (21 AtA + 6 Atb + sum b^2 + n_valid) are all-reduced; all ranks
+ * then solve the identical 6x6 system.  d_match_out (may be NULL): ns u32, matched target index
+ * per source point of this rank (TC_NO_INDEX = rejected), original source order. */
+int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                                 const tc_index* tgt_index, const float* d_tgt_normals_aos,
+                                 const float init[7], uint32_t max_iters, float max_corr_dist,
+                                 float conv_threshold, tc_icp_result* out, uint32_t* d_match_out);
+
+/* ---- multi-GPU (one process per GPU; NCCL bootstrap, id exchanged out of band) ------------- */
+#define TC_COMM_ID_BYTES 128
+int tc_comm_get_unique_id(tc_context* ctx, void* id_out /* TC_COMM_ID_BYTES */);
+int tc_comm_init_rank(tc_context* ctx, const void* id, int n_ranks, int rank, tc_comm** out);
+void tc_comm_destroy(tc_comm* comm);
+/* Sum-all-reduce of `count` f64 on the context's stream (exposed for tests). */
+int tc_comm_allreduce_f64(tc_comm* comm, double* d_buf, uint64_t count);
+
+/* ---- raw device memory helpers for hosts without their own CUDA bindings ------------------- */
+int tc_device_alloc(tc_context* ctx, uint64_t bytes, void** d_out);
+int tc_device_free(tc_context* ctx, void* d_ptr);
+int tc_copy_to_device(tc_context* ctx, void* d_dst, const void* h_src, uint64_t bytes);
+int tc_copy_to_host(tc_context* ctx, void* h_dst, const void* d_src, uint64_t bytes);
+/* Page-locked host memory (so uploads/readbacks run at PCIe rate and asynchronously). */
+int tc_host_alloc_pinned(uint64_t bytes, void** h_out);
+int tc_host_free_pinned(void* h_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THREECRATE_CUDA_H */

@@ -1,0 +1,114 @@
+"""GPU point-to-plane ICP parity against the oracle: transforms within 1e-5 in rotation (rad)
+and translation (north-star tolerance), through the C ABI."""
+import numpy as np
+import pytest
+
+import threecrate_b200 as tc
+from threecrate_b200 import synth
+from gpu_util import quat_angle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # north_star: "ICP transforms within 1e-5 in rotation and translation"
+
+
+def _compare(got, ref, check_pairs=True):
+    rot = quat_angle(got.rotation, ref.rotation)
+    tr = float(np.linalg.norm(got.translation.astype(np.float64) - ref.translation))
+    print(f"ICP parity: rot_err={rot:.3e} rad  trans_err={tr:.3e}  iters={got.iterations}/"
+          f"{ref.iterations} mse={got.mse:.6e}/{ref.mse:.6e}")
+    assert rot <= TOL and tr <= TOL
+    assert got.iterations == ref.iterations and got.converged == ref.converged
+    assert abs(got.mse - ref.mse) <= 1e-4 * max(abs(ref.mse), 1e-12) + 1e-12
+    if check_pairs:
+        assert len(got.correspondences) == len(ref.correspondences)
+
+
+def test_reference_fixture_identity(orc):
+    # registration.rs:1167-1177
+    p, n = synth.fibonacci_sphere(50)
+    r = tc.icp_point_to_plane(p, p, n, tc.IDENTITY, 20)
+    assert r.converged and r.mse < 1e-6
+    _compare(r, orc.icp_point_to_plane(p, p, n, max_iters=20))
+
+
+def test_reference_fixture_translation(orc):
+    # registration.rs:1179-1196
+    p, n = synth.fibonacci_sphere(100)
+    shift = np.array([0.15, 0, 0], np.float32)
+    r = tc.icp_point_to_plane(p, p + shift, n, tc.IDENTITY, 50)
+    assert np.linalg.norm(r.translation - shift) < 0.3 and r.mse < 0.1
+    ref = orc.icp_point_to_plane(p, p + shift, n, max_iters=50)
+    _compare(r, ref)
+    assert np.array_equal(r.correspondences, ref.correspondences)
+
+
+def test_reference_fixture_validation():
+    # registration.rs:1198-1216 (+ order of checks :517-531)
+    p, n = synth.fibonacci_sphere(20)
+    with pytest.raises(tc.InvalidData):
+        tc.icp_point_to_plane(p, p, np.array([[0, 0, 1]], np.float32), tc.IDENTITY, 10)
+    with pytest.raises(tc.InvalidData):
+        tc.icp_point_to_plane(np.zeros((0, 3), np.float32), p, n, tc.IDENTITY, 10)
+    with pytest.raises(tc.InvalidData):
+        tc.icp_point_to_plane_detailed(p, p, n, tc.IDENTITY, 0, None, 1e-6)
+
+
+def test_reference_fixture_max_distance(orc):
+    # registration.rs:1253-1267
+    p, n = synth.fibonacci_sphere(50)
+    tgt = p + np.array([0.1, 0, 0], np.float32)
+    r = tc.icp_point_to_plane_detailed(p, tgt, n, tc.IDENTITY, 30, 5.0, 1e-6)
+    assert r.mse < 0.5
+    _compare(r, orc.icp_point_to_plane(p, tgt, n, max_iters=30, max_dist=5.0))
+
+
+def test_insufficient_correspondences_is_algorithm_error():
+    # registration.rs:568-572
+    p, n = synth.fibonacci_sphere(50)
+    with pytest.raises(tc.AlgorithmError):
+        tc.icp_point_to_plane_detailed(p, p + np.float32(100.0), n, tc.IDENTITY, 5, 0.5, 1e-6)
+
+
+def test_nonidentity_init_and_not_converged_semantics(orc):
+    p, n = synth.fibonacci_sphere(100)
+    tgt = p + np.array([0.1, 0.05, 0], np.float32)
+    init = np.concatenate([[0.02, 0.0, -0.01], synth.quat_from_euler(0.0, 0.01, 0.0)]).astype(np.float32)
+    r = tc.icp_point_to_plane_detailed(p, tgt, n, init, 7, None, -1.0)  # conv <= 0: never converges
+    ref = orc.icp_point_to_plane(p, tgt, n, init=init, max_iters=7, conv=-1.0)
+    assert not r.converged and r.iterations == 7
+    _compare(r, ref)
+
+
+@pytest.mark.parametrize("copy_variant", [True, False])
+def test_parity_scan_pair_fixed_30_iterations(orc, copy_variant):
+    """C3-shaped (scaled to 100k so the serial oracle finishes in seconds); conv=-1 forces 30."""
+    src, tgt, nrm, T = synth.scan_pair(100_000, half_extent=16.0, copy_variant=copy_variant)
+    r = tc.icp_point_to_plane_detailed(src, tgt, nrm, tc.IDENTITY, 30, None, -1.0)
+    ref = orc.icp_point_to_plane(src, tgt, nrm, max_iters=30, conv=-1.0)
+    _compare(r, ref)
+    same = (r.correspondences == ref.correspondences).all(axis=1).mean()
+    print(f"correspondence agreement: {same:.6f}")
+    assert same > 0.9999
+    assert np.linalg.norm(r.translation - T[:3]) < 5e-3
+
+
+def test_parity_scan_pair_default_convergence(orc):
+    src, tgt, nrm, T = synth.scan_pair(60_000, half_extent=12.0, copy_variant=True)
+    r = tc.icp_point_to_plane(src, tgt, nrm, tc.IDENTITY, 30)
+    ref = orc.icp_point_to_plane(src, tgt, nrm, max_iters=30)
+    _compare(r, ref)
+
+
+def test_full_size_c3_properties():
+    """C3 at full size (1M <-> 1M): recovers the known rigid offset; idempotent at the solution."""
+    src, tgt, nrm, T = synth.scan_pair(1_000_000, half_extent=50.0, copy_variant=True)
+    r = tc.icp_point_to_plane_detailed(src, tgt, nrm, tc.IDENTITY, 30, None, -1.0,
+                                       want_correspondences=False)
+    assert r.iterations == 30
+    assert np.linalg.norm(r.translation - T[:3]) < 1e-3
+    assert quat_angle(r.rotation, T[3:]) < 1e-4
+    # restarting from the answer stays there (fixed point) and converges immediately
+    r2 = tc.icp_point_to_plane_detailed(src, tgt, nrm, r.transformation, 5, None, 1e-6,
+                                        want_correspondences=False)
+    assert np.linalg.norm(r2.translation - r.translation) < 1e-4
+    assert r2.converged

@@ -1,0 +1,137 @@
+"""GPU kNN parity (bit-exact indices) against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import threecrate_b200 as tc
+from threecrate_b200 import synth
+from gpu_util import knn_parity
+
+pytestmark = pytest.mark.gpu
+NO = 0xFFFFFFFF
+
+
+def _brute(orc, pts, q, k):
+    return orc.brute_knn(pts, q, k)
+
+
+def test_cube_ties_follow_the_canonical_rule(orc):
+    # nearest_neighbor.rs:429-436 fixture: every corner is at d2 = 0.75 from the centre
+    t = tc.KdTree(synth.cube8())
+    idx, dist = t.find_k_nearest([0.5, 0.5, 0.5], 3)
+    assert idx.tolist() == [0, 1, 2]  # ascending (d2, index)
+    assert np.all(dist == np.sqrt(np.float32(0.75)))
+
+
+def test_edge_cases():
+    t = tc.KdTree(synth.cube8())
+    assert len(t.find_k_nearest([0, 0, 0], 0)[0]) == 0          # k == 0
+    idx, dist = t.find_k_nearest([0, 0, 0], 20)                  # k > n -> n results
+    assert len(idx) == 8 and np.all(np.diff(dist) >= 0) and idx[0] == 0
+    e = tc.KdTree(np.zeros((0, 3), np.float32))
+    assert len(e.find_k_nearest([0, 0, 0], 3)[0]) == 0          # empty tree
+    one = tc.KdTree(np.array([[1, 2, 3]], np.float32))
+    idx, dist = one.find_k_nearest([1, 2, 4], 5)
+    assert idx.tolist() == [0] and dist[0] == 1.0
+    with pytest.raises(tc.InvalidData):
+        tc.KdTree(np.array([[np.nan, 0, 0]], np.float32))
+
+
+@pytest.mark.parametrize("n,k", [(1000, 1), (5000, 5), (20000, 16), (20000, 30)])
+def test_external_queries_bit_exact_vs_bruteforce(orc, n, k):
+    rng = np.random.default_rng(n + k)
+    pts = rng.uniform(-10, 10, (n, 3)).astype(np.float32)
+    q = rng.uniform(-12, 12, (700, 3)).astype(np.float32)  # some queries outside the bbox
+    q[:5] = [[100, 100, 100], [-50, 0, 0], [0, 0, 37], [10, 10, 10], [-10, -10, -10]]
+    idx, dist, cnt = tc.KdTree(pts).knn(q, k)
+    bi, bd2 = _brute(orc, pts, q, k)
+    assert np.all(cnt == k)
+    assert np.array_equal(idx.astype(np.uint64), bi)
+    assert np.array_equal(dist, np.sqrt(bd2))  # bitwise: sqrt of identical d2
+
+
+def test_self_knn_excludes_self_bit_exact(orc):
+    rng = np.random.default_rng(5)
+    pts = rng.normal(size=(15000, 3)).astype(np.float32)
+    k = 16
+    idx, dist, cnt = tc.k_nearest_neighbors(pts, k)
+    bi, bd2 = _brute(orc, pts, pts, k + 1)
+    assert np.all(cnt == k)
+    assert np.all(bi[:, 0] == np.arange(len(pts)))  # self first (d2 = 0, no duplicates)
+    assert np.array_equal(idx.astype(np.uint64), bi[:, 1:])
+    assert np.array_equal(dist, np.sqrt(bd2[:, 1:]))
+
+
+def test_tie_dense_grid_matches_canonical_rule_exactly(orc):
+    pts = synth.grid_plane(20, 0.1)
+    idx, dist, cnt = tc.KdTree(pts).knn(pts, 9)
+    bi, bd2 = _brute(orc, pts, pts, 9)
+    assert np.array_equal(idx.astype(np.uint64), bi)
+    # and agrees with the reference kd-tree modulo ties
+    ki, kd2, _ = orc.OracleKdTree(pts).knn_batch(pts, 9)
+    exact, modulo, mismatch = knn_parity(idx, dist, ki, kd2, pts, pts)
+    assert not mismatch and modulo > 0
+
+
+def test_duplicates_and_small_clouds(orc):
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 3, (400, 3)).astype(np.float32)  # many exact duplicates
+    idx, dist, cnt = tc.k_nearest_neighbors(base, 7)
+    bi, bd2 = _brute(orc, base, base, 8)
+    for i in range(len(base)):  # k+1 search, drop own index, keep 7
+        exp = [j for j in bi[i].tolist() if j != i][:7]
+        assert idx[i].tolist() == exp
+    # fewer points than k: n-1 neighbours, padded
+    small = rng.normal(size=(5, 3)).astype(np.float32)
+    idx, dist, cnt = tc.k_nearest_neighbors(small, 10)
+    assert np.all(cnt == 4) and np.all(idx[:, 4:] == NO) and np.all(np.isinf(dist[:, 4:]))
+
+
+def test_kitti_frame_k16_vs_reference_kdtree(orc):
+    """BASELINE config 2: indices bit-exact vs the kd-tree restatement (modulo documented ties)."""
+    pts = synth.kitti_frame()
+    k = 16
+    idx, dist, cnt = tc.k_nearest_neighbors(pts, k)
+    ri, rdist, rcnt = orc.k_nearest_neighbors(pts, k, threads=0)
+    assert np.all(cnt == k)
+    rd2 = (rdist * rdist).astype(np.float32)
+    exact, modulo, mismatch = knn_parity(idx, dist, ri, rd2, pts, pts)
+    print(f"kNN C2: exact={exact} modulo_ties={modulo} mismatch={len(mismatch)}")
+    assert not mismatch
+    assert exact > 0.999 * len(pts)
+    assert np.array_equal(dist[idx == ri.astype(np.uint32)], rdist[idx == ri.astype(np.uint32)])
+
+
+def test_clustered_and_skewed_density(orc):
+    """Ring expansion: dense blob + isolated far points + a line (degenerate extents)."""
+    rng = np.random.default_rng(21)
+    blob = rng.normal(scale=0.01, size=(4000, 3))
+    far = rng.uniform(-50, 50, (60, 3))
+    line = np.stack([np.linspace(-5, 5, 500), np.zeros(500), np.zeros(500)], 1)
+    pts = np.concatenate([blob, far, line]).astype(np.float32)
+    q = np.concatenate([pts[::7], rng.uniform(-60, 60, (100, 3)).astype(np.float32)])
+    idx, dist, cnt = tc.KdTree(pts).knn(q, 11)
+    bi, bd2 = _brute(orc, pts, q, 11)
+    assert np.array_equal(idx.astype(np.uint64), bi)
+    # all points on a plane / line / single point
+    for cloud in (line.astype(np.float32), np.repeat(np.array([[1, 1, 1]], np.float32), 50, 0)):
+        idx, dist, cnt = tc.KdTree(cloud).knn(cloud[:20], 5)
+        bi, bd2 = _brute(orc, cloud, cloud[:20], 5)
+        assert np.array_equal(idx.astype(np.uint64), bi)
+
+
+def test_full_size_properties_1m():
+    """Size-independent properties at 1M points: ascending rows, no self, symmetric sanity."""
+    pts = synth.terrain(1_000_000, 50.0, seed=1)
+    cloud = tc.DeviceCloud(pts)
+    index = tc.GridIndex(cloud, k_hint=16)
+    idx, dist, cnt = index.knn(None, 16, exclude_self=True)
+    assert np.all(cnt == 16)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    assert not np.any(idx == np.arange(len(pts), dtype=np.uint32)[:, None])
+    # distances recompute bit-exactly from the returned indices
+    sel = np.random.default_rng(0).integers(0, len(pts), 2000)
+    d = pts[idx[sel]] - pts[sel][:, None, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    assert np.array_equal(np.sqrt(d2.astype(np.float32)), dist[sel])
+    info = index.info()
+    assert info["n_points"] == len(pts) and info["occupied_cells"] > 0

@@ -1,0 +1,37 @@
+"""threecrate_b200 — B200-native (sm_100a) kNN -> normals -> point-to-plane ICP hot path of
+rajgandhi1/threecrate, behind the reference's operator interface.
+
+  csrc/      hand-written CUDA kernels + the C ABI (include/threecrate_cuda.h)
+  api.py     host-side mirror of the reference functions (ctypes over the C ABI)
+  synth.py   deterministic synthetic clouds for the BASELINE.json configs
+  build.py   in-tree nvcc build of lib/libthreecrate_cuda.so
+
+The CUDA library is the only compute path: importing `api` symbols works on a CPU box (for
+argument validation and symbol checks), but any compute call without the built library or a
+CUDA device raises GpuError.
+"""
+from .api import (  # noqa: F401
+    AlgorithmError,
+    Comm,
+    Context,
+    DeviceCloud,
+    GpuError,
+    GridIndex,
+    ICPResult,
+    IDENTITY,
+    InvalidData,
+    KdTree,
+    NormalEstimationConfig,
+    ThreecrateError,
+    default_context,
+    estimate_normals,
+    estimate_normals_radius,
+    estimate_normals_with_config,
+    icp_point_to_plane,
+    icp_point_to_plane_detailed,
+    icp_point_to_plane_device,
+    k_nearest_neighbors,
+    pinned_empty,
+)
+
+__version__ = "0.1.0"

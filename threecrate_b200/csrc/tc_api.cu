@@ -1,0 +1,455 @@
+// tc_api.cu — C ABI glue: context, device-resident cloud, and the host-buffer entry points that
+// mirror the reference's public functions (see include/threecrate_cuda.h for the citations).
+#include <cstring>
+#include <vector>
+
+#include "tc_internal.cuh"
+
+#define TC_ENTER(ctx)                                   \
+  do {                                                  \
+    if (!(ctx)) return TC_INVALID_DATA;                 \
+    TC_CUDA((ctx), cudaSetDevice((ctx)->device));       \
+  } while (0)
+
+extern "C" const char* tc_version(void) { return "threecrate_cuda 0.1.0 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int tc_context_create(int device, tc_context** out) {
+  if (!out) return TC_INVALID_DATA;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return TC_GPU;  // no CUDA device: there is no CPU fallback
+  }
+  tc_context* ctx = new tc_context();
+  ctx->device = device;
+  auto fail = [&](const char* what) {
+    fprintf(stderr, "tc_context_create: %s failed: %s\n", what,
+            cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return (int)TC_GPU;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail("cudaStreamCreate");
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
+    return fail("cudaEventCreate");
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMalloc((void**)&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
+    return fail("cudaMalloc");
+  if (cudaMallocHost((void**)&ctx->h_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
+    return fail("cudaMallocHost");
+  // keep freed blocks cached in the stream-ordered pool: no cudaMalloc/cudaFree per call
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return TC_OK;
+}
+
+extern "C" void tc_context_destroy(tc_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* tc_last_error(const tc_context* ctx) { return ctx ? ctx->err.c_str() : ""; }
+extern "C" void* tc_context_stream(tc_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t tc_launch_count(const tc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int tc_context_synchronize(tc_context* ctx) {
+  TC_ENTER(ctx);
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TC_OK;
+}
+extern "C" int tc_timer_start(tc_context* ctx) {
+  TC_ENTER(ctx);
+  TC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return TC_OK;
+}
+extern "C" int tc_timer_stop(tc_context* ctx, float* ms_out) {
+  TC_ENTER(ctx);
+  TC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  TC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  float ms = 0.0f;
+  TC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (ms_out) *ms_out = ms;
+  return TC_OK;
+}
+
+// ------------------------------------------------------------------------------ memory helpers
+extern "C" int tc_device_alloc(tc_context* ctx, uint64_t bytes, void** d_out) {
+  TC_ENTER(ctx);
+  if (!d_out) return TC_INVALID_DATA;
+  uint8_t* p = nullptr;
+  TC_TRY(tc_alloc(ctx, &p, bytes));
+  *d_out = p;
+  return TC_OK;
+}
+extern "C" int tc_device_free(tc_context* ctx, void* d_ptr) {
+  TC_ENTER(ctx);
+  tc_free(ctx, d_ptr);
+  return TC_OK;
+}
+extern "C" int tc_copy_to_device(tc_context* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
+  TC_ENTER(ctx);
+  if (bytes == 0) return TC_OK;
+  TC_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return TC_OK;
+}
+extern "C" int tc_copy_to_host(tc_context* ctx, void* h_dst, const void* d_src, uint64_t bytes) {
+  TC_ENTER(ctx);
+  if (bytes == 0) return TC_OK;
+  TC_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TC_OK;
+}
+extern "C" int tc_host_alloc_pinned(uint64_t bytes, void** h_out) {
+  if (!h_out) return TC_INVALID_DATA;
+  *h_out = nullptr;
+  if (cudaMallocHost(h_out, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return TC_GPU;
+  }
+  return TC_OK;
+}
+extern "C" int tc_host_free_pinned(void* h_ptr) {
+  if (h_ptr && cudaFreeHost(h_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return TC_GPU;
+  }
+  return TC_OK;
+}
+
+// -------------------------------------------------------------------------------------- cloud
+namespace {
+__global__ void k_destride(const uint8_t* __restrict__ src, uint64_t n, uint32_t stride,
+                           float* __restrict__ dst) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(src + i * stride);
+    dst[3 * i + 0] = p[0];
+    dst[3 * i + 1] = p[1];
+    dst[3 * i + 2] = p[2];
+  }
+}
+}  // namespace
+
+extern "C" int tc_cloud_upload(tc_context* ctx, const float* xyz_aos, uint64_t n, tc_cloud** out) {
+  TC_ENTER(ctx);
+  if (!out || (n > 0 && !xyz_aos)) return TC_INVALID_DATA;
+  *out = nullptr;
+  if (n >= 0xFFFFFFFFull) return tc_fail(ctx, TC_INVALID_DATA, "cloud too large (N < 2^32-1)");
+  tc_cloud* c = new tc_cloud();
+  c->ctx = ctx;
+  c->n = n;
+  int st = tc_alloc(ctx, &c->d_xyz, 3 * n);
+  if (st == TC_OK && n > 0) {
+    if (cudaMemcpyAsync(c->d_xyz, xyz_aos, 3 * n * sizeof(float), cudaMemcpyHostToDevice,
+                        ctx->stream) != cudaSuccess)
+      st = tc_fail(ctx, TC_GPU, "cloud upload failed");
+  }
+  if (st != TC_OK) {
+    tc_cloud_free(c);
+    return st;
+  }
+  *out = c;
+  return TC_OK;
+}
+
+extern "C" int tc_cloud_upload_strided(tc_context* ctx, const void* base, uint64_t n,
+                                       uint32_t stride_bytes, tc_cloud** out) {
+  TC_ENTER(ctx);
+  if (!out || (n > 0 && !base)) return TC_INVALID_DATA;
+  if (stride_bytes < 12 || (stride_bytes & 3u))
+    return tc_fail(ctx, TC_INVALID_DATA, "stride must be a multiple of 4 and at least 12 bytes");
+  if (stride_bytes == 12) return tc_cloud_upload(ctx, (const float*)base, n, out);
+  *out = nullptr;
+  if (n >= 0xFFFFFFFFull) return tc_fail(ctx, TC_INVALID_DATA, "cloud too large (N < 2^32-1)");
+  tc_cloud* c = new tc_cloud();
+  c->ctx = ctx;
+  c->n = n;
+  uint8_t* d_raw = nullptr;
+  int st = tc_alloc(ctx, &c->d_xyz, 3 * n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_raw, n * stride_bytes);
+  if (st == TC_OK && n > 0) {
+    // raw records go up in one copy and are de-interleaved on the device
+    if (cudaMemcpyAsync(d_raw, base, n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream) !=
+        cudaSuccess)
+      st = tc_fail(ctx, TC_GPU, "cloud upload failed");
+    if (st == TC_OK) {
+      const int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+      k_destride<<<blocks, 256, 0, ctx->stream>>>(d_raw, n, stride_bytes, c->d_xyz);
+      ctx->launches++;
+    }
+  }
+  tc_free(ctx, d_raw);
+  if (st != TC_OK) {
+    tc_cloud_free(c);
+    return st;
+  }
+  *out = c;
+  return TC_OK;
+}
+
+extern "C" int tc_cloud_from_device(tc_context* ctx, const float* d_xyz_aos, uint64_t n,
+                                    tc_cloud** out) {
+  TC_ENTER(ctx);
+  if (!out || (n > 0 && !d_xyz_aos)) return TC_INVALID_DATA;
+  *out = nullptr;
+  if (n >= 0xFFFFFFFFull) return tc_fail(ctx, TC_INVALID_DATA, "cloud too large (N < 2^32-1)");
+  tc_cloud* c = new tc_cloud();
+  c->ctx = ctx;
+  c->n = n;
+  int st = tc_alloc(ctx, &c->d_xyz, 3 * n);
+  if (st == TC_OK && n > 0 &&
+      cudaMemcpyAsync(c->d_xyz, d_xyz_aos, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice,
+                      ctx->stream) != cudaSuccess)
+    st = tc_fail(ctx, TC_GPU, "device copy failed");
+  if (st != TC_OK) {
+    tc_cloud_free(c);
+    return st;
+  }
+  *out = c;
+  return TC_OK;
+}
+
+extern "C" void tc_cloud_free(tc_cloud* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  tc_free(c->ctx, c->d_xyz);
+  delete c;
+}
+extern "C" uint64_t tc_cloud_len(const tc_cloud* c) { return c ? c->n : 0; }
+
+// ---------------------------------------------------------------------------------------- kNN
+extern "C" int tc_knn_device(tc_context* ctx, const tc_index* ix, const float* d_queries_aos,
+                             uint64_t nq, uint32_t k, int exclude_self, uint32_t* d_idx_out,
+                             float* d_dist_out, uint32_t* d_count_out) {
+  TC_ENTER(ctx);
+  if (!ix) return TC_INVALID_DATA;
+  const bool self_query = (d_queries_aos == nullptr);
+  if (self_query && nq != ix->n)
+    return tc_fail(ctx, TC_INVALID_DATA, "self query: nq must equal the indexed cloud's length");
+  if (nq == 0) return TC_OK;
+  if (k == 0 || ix->n == 0) {  // nearest_neighbor.rs:178-180
+    if (d_count_out) TC_CUDA(ctx, cudaMemsetAsync(d_count_out, 0, nq * sizeof(uint32_t), ctx->stream));
+    return TC_OK;
+  }
+  if (!d_idx_out) return TC_INVALID_DATA;
+  if (self_query)
+    return tci_knn_launch(ctx, ix, ix->d_pts, 0, nq, k, exclude_self, true, d_idx_out, d_dist_out,
+                          d_count_out);
+  // external queries: validate + sort by the index's grid for warp coherence
+  float mn[3], mx[3];
+  TC_TRY(tci_bbox(ctx, d_queries_aos, nq, mn, mx));
+  float4* d_sorted = nullptr;
+  TC_TRY(tci_sort_by_grid(ctx, d_queries_aos, nq, ix->g, &d_sorted));
+  const int st = tci_knn_launch(ctx, ix, d_sorted, 0, nq, k, 0, false, d_idx_out, d_dist_out,
+                                d_count_out);
+  tc_free(ctx, d_sorted);
+  return st;
+}
+
+extern "C" int tc_knn(tc_context* ctx, const tc_index* ix, const float* queries_aos, uint64_t nq,
+                      uint32_t k, int exclude_self, uint32_t* idx_out, float* dist_out,
+                      uint32_t* count_out) {
+  TC_ENTER(ctx);
+  if (!ix) return TC_INVALID_DATA;
+  if (nq == 0) return TC_OK;
+  if (k == 0 || ix->n == 0) {
+    if (count_out) memset(count_out, 0, nq * sizeof(uint32_t));
+    return TC_OK;
+  }
+  if (!idx_out) return TC_INVALID_DATA;
+  float* d_q = nullptr;
+  uint32_t *d_idx = nullptr, *d_cnt = nullptr;
+  float* d_dist = nullptr;
+  int st = TC_OK;
+  if (queries_aos) {
+    st = tc_alloc(ctx, &d_q, 3 * nq);
+    if (st == TC_OK &&
+        cudaMemcpyAsync(d_q, queries_aos, 3 * nq * sizeof(float), cudaMemcpyHostToDevice,
+                        ctx->stream) != cudaSuccess)
+      st = tc_fail(ctx, TC_GPU, "query upload failed");
+  }
+  if (st == TC_OK) st = tc_alloc(ctx, &d_idx, nq * k);
+  if (st == TC_OK && dist_out) st = tc_alloc(ctx, &d_dist, nq * k);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_cnt, nq);
+  if (st == TC_OK) st = tc_knn_device(ctx, ix, d_q, nq, k, exclude_self, d_idx, d_dist, d_cnt);
+  if (st == TC_OK) {
+    cudaError_t e = cudaMemcpyAsync(idx_out, d_idx, nq * k * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && dist_out)
+      e = cudaMemcpyAsync(dist_out, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost,
+                          ctx->stream);
+    if (e == cudaSuccess && count_out)
+      e = cudaMemcpyAsync(count_out, d_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = tc_fail(ctx, TC_GPU, std::string("kNN: ") + cudaGetErrorString(e));
+  }
+  tc_free(ctx, d_q);
+  tc_free(ctx, d_idx);
+  tc_free(ctx, d_dist);
+  tc_free(ctx, d_cnt);
+  return st;
+}
+
+extern "C" int tc_radius_search(tc_context* ctx, const tc_index* ix, const float query[3],
+                                float radius, uint32_t* idx_out, float* dist_out, uint64_t capacity,
+                                uint64_t* n_found) {
+  TC_ENTER(ctx);
+  (void)ix; (void)query; (void)radius; (void)idx_out; (void)dist_out; (void)capacity;
+  if (n_found) *n_found = 0;
+  return tc_fail(ctx, TC_GPU, "tc_radius_search: not implemented on the device path yet");
+}
+
+// ------------------------------------------------------------------------------------ normals
+namespace {
+// default viewpoint (normals.rs:275-303), f32 arithmetic in the reference's order
+void default_viewpoint(const float mn[3], const float mx[3], float vp[3]) {
+  const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+  volatile float e2 = ex * ex;
+  volatile float t = ey * ey;
+  e2 = e2 + t;
+  t = ez * ez;
+  e2 = e2 + t;
+  const float extent = sqrtf(e2);
+  vp[0] = (mn[0] + mx[0]) / 2.0f;
+  vp[1] = (mn[1] + mx[1]) / 2.0f;
+  vp[2] = (mn[2] + mx[2]) / 2.0f + extent;
+}
+}  // namespace
+
+extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, uint32_t k,
+                                          float radius, int consistent_orientation,
+                                          const float* viewpoint3, uint64_t shard_begin,
+                                          uint64_t shard_end, float* d_out_aos) {
+  TC_ENTER(ctx);
+  if (!ix) return TC_INVALID_DATA;
+  if (ix->n == 0) return TC_OK;  // empty -> Ok(empty), checked before k (normals.rs:261-263)
+  if (k < 3) return tc_fail(ctx, TC_INVALID_DATA, "k_neighbors must be at least 3");
+  if (radius >= 0.0f)
+    return tc_fail(ctx, TC_GPU, "radius-mode normals are not implemented on the device path yet");
+  if (!d_out_aos) return TC_INVALID_DATA;
+  if (shard_end > ix->n) shard_end = ix->n;
+  float vp[3];
+  if (viewpoint3) {
+    vp[0] = viewpoint3[0];
+    vp[1] = viewpoint3[1];
+    vp[2] = viewpoint3[2];
+  } else {
+    default_viewpoint(ix->bbox_min, ix->bbox_max, vp);
+  }
+  return tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, shard_begin, shard_end,
+                            d_out_aos);
+}
+
+extern "C" int tc_estimate_normals_indexed(tc_context* ctx, const tc_index* ix, uint32_t k,
+                                           float radius, int consistent_orientation,
+                                           const float* viewpoint3, float* out_aos) {
+  TC_ENTER(ctx);
+  if (!ix) return TC_INVALID_DATA;
+  if (ix->n == 0) return TC_OK;
+  if (k < 3) return tc_fail(ctx, TC_INVALID_DATA, "k_neighbors must be at least 3");
+  if (!out_aos) return TC_INVALID_DATA;
+  float* d_out = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_out, 6 * ix->n));
+  int st = tc_estimate_normals_device(ctx, ix, k, radius, consistent_orientation, viewpoint3, 0,
+                                      ix->n, d_out);
+  if (st == TC_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_aos, d_out, 6 * ix->n * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = tc_fail(ctx, TC_GPU, std::string("normals: ") + cudaGetErrorString(e));
+  }
+  tc_free(ctx, d_out);
+  return st;
+}
+
+extern "C" int tc_estimate_normals(tc_context* ctx, const float* xyz_aos, uint64_t n, uint32_t k,
+                                   float radius, int consistent_orientation,
+                                   const float* viewpoint3, float* out_aos) {
+  TC_ENTER(ctx);
+  if (n == 0) return TC_OK;  // normals.rs:261-263
+  if (k < 3) return tc_fail(ctx, TC_INVALID_DATA, "k_neighbors must be at least 3");
+  if (!xyz_aos || !out_aos) return TC_INVALID_DATA;
+  tc_cloud* cloud = nullptr;
+  tc_index* ix = nullptr;
+  int st = tc_cloud_upload(ctx, xyz_aos, n, &cloud);
+  if (st == TC_OK) st = tc_index_build(ctx, cloud, k, 0.0f, &ix);
+  if (st == TC_OK)
+    st = tc_estimate_normals_indexed(ctx, ix, k, radius, consistent_orientation, viewpoint3,
+                                     out_aos);
+  tc_index_free(ix);
+  tc_cloud_free(cloud);
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------- ICP
+extern "C" int tc_icp_point_to_plane(tc_context* ctx, const float* src_aos, uint64_t ns,
+                                     const float* tgt_aos, uint64_t nt,
+                                     const float* tgt_normals_aos, uint64_t n_normals,
+                                     const float init[7], uint32_t max_iters, float max_corr_dist,
+                                     float conv_threshold, tc_icp_result* out,
+                                     uint64_t* pairs_out) {
+  TC_ENTER(ctx);
+  // validation order of registration.rs:517-531
+  if (ns == 0 || nt == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
+  if (n_normals != nt)
+    return tc_fail(ctx, TC_INVALID_DATA,
+                   "target_normals length must equal the number of target points");
+  if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
+  if (!src_aos || !tgt_aos || !tgt_normals_aos || !init || !out) return TC_INVALID_DATA;
+  tc_cloud *src = nullptr, *tgt = nullptr;
+  tc_index* ix = nullptr;
+  float* d_nrm = nullptr;
+  uint32_t* d_match = nullptr;
+  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
+  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_nrm, 3 * nt);
+  if (st == TC_OK &&
+      cudaMemcpyAsync(d_nrm, tgt_normals_aos, 3 * nt * sizeof(float), cudaMemcpyHostToDevice,
+                      ctx->stream) != cudaSuccess)
+    st = tc_fail(ctx, TC_GPU, "normals upload failed");
+  if (st == TC_OK) st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);  // KdTree::new(target), :536
+  if (st == TC_OK && pairs_out) st = tc_alloc(ctx, &d_match, ns);
+  if (st == TC_OK)
+    st = tc_icp_point_to_plane_device(ctx, nullptr, src, ix, d_nrm, init, max_iters, max_corr_dist,
+                                      conv_threshold, out, d_match);
+  if (st == TC_OK && pairs_out) {
+    std::vector<uint32_t> match(ns);
+    cudaError_t e = cudaMemcpyAsync(match.data(), d_match, ns * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      st = tc_fail(ctx, TC_GPU, std::string("ICP pairs: ") + cudaGetErrorString(e));
+    } else {
+      uint64_t c = 0;
+      for (uint64_t i = 0; i < ns; ++i)
+        if (match[i] != TC_NO_INDEX) {
+          pairs_out[2 * c] = i;
+          pairs_out[2 * c + 1] = match[i];
+          ++c;
+        }
+      out->n_correspondences = c;
+    }
+  }
+  tc_free(ctx, d_match);
+  tc_free(ctx, d_nrm);
+  tc_index_free(ix);
+  tc_cloud_free(tgt);
+  tc_cloud_free(src);
+  return st;
+}

@@ -1,0 +1,396 @@
+// tc_icp.cu — point-to-plane ICP with the whole iteration loop resident on the device.
+//
+// Replaces icp_point_to_plane_detailed (threecrate-algorithms/src/registration.rs:508-602):
+//   transform (serial map, :540-544) + kd-tree 1-NN (rayon, :87-107) + serial gather (:553-565) +
+//   serial 6x6 accumulation (:412-428) + Cholesky/LU (:432-438) + compose (:441-449,576) + mse
+//   (:453-471) + convergence test (:579-589).
+//
+// Per iteration two launches and no host round-trip:
+//   k_icp_correspond : one thread per source point (grid-stride): T*p with nalgebra's f32 op order,
+//                      exact grid 1-NN (tie rule (d2, index)), linearise, accumulate the 29 scalars
+//                      (21 AtA + 6 Atb + sum b^2 + n_valid) in f64 registers, warp-shuffle + block
+//                      reduce, last block sums the block partials in block order (deterministic).
+//   [multi-GPU: NCCL all-reduce of the 29 f64 on the same stream]
+//   k_icp_solve      : one thread: 6x6 Cholesky (LU fallback), delta = Rz Ry Rx, T <- delta o T,
+//                      mse, convergence flag.  Later iterations early-exit once `done` is set.
+#include "tc_search.cuh"
+
+struct tc_comm;
+int tci_comm_allreduce(tc_comm* comm, double* d_buf, uint64_t count);  // tc_comm.cu
+
+namespace {
+
+using namespace tcs;
+
+constexpr int kIcpBlock = 256;
+constexpr int kNumSums = 29;  // 21 + 6 + 1 + 1
+
+struct IcpState {
+  float T[7];          // tx,ty,tz, qi,qj,qk,qw
+  float prev_mse;
+  float mse;
+  uint32_t iterations; // iterations executed so far
+  int32_t converged;
+  int32_t status;      // 0 ok, 2 insufficient correspondences, 3 ill-conditioned
+  int32_t done;
+  uint32_t ticket;     // block completion counter
+  double n_valid;
+};
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 xcross(const V3& a, const V3& b) {
+  return V3{xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)),
+            xsub(xmul(a.x, b.y), xmul(a.y, b.x))};
+}
+// nalgebra UnitQuaternion * Vector3:  t = 2 (qv x v);  (t*w + qv x t) + v   [upstream nalgebra]
+__device__ __forceinline__ V3 quat_rotate(const float q[4] /*i,j,k,w*/, const V3& v) {
+  const V3 qv{q[0], q[1], q[2]};
+  V3 t = xcross(qv, v);
+  t = V3{xmul(t.x, 2.0f), xmul(t.y, 2.0f), xmul(t.z, 2.0f)};
+  const V3 c = xcross(qv, t);
+  return V3{xadd(xadd(xmul(t.x, q[3]), c.x), v.x), xadd(xadd(xmul(t.y, q[3]), c.y), v.y),
+            xadd(xadd(xmul(t.z, q[3]), c.z), v.z)};
+}
+__device__ __forceinline__ void quat_mul(const float a[4], const float b[4], float r[4]) {
+  // Hamilton product, left-to-right evaluation, no renormalisation  [upstream nalgebra]
+  r[3] = xsub(xsub(xsub(xmul(a[3], b[3]), xmul(a[0], b[0])), xmul(a[1], b[1])), xmul(a[2], b[2]));
+  r[0] = xsub(xadd(xadd(xmul(a[3], b[0]), xmul(a[0], b[3])), xmul(a[1], b[2])), xmul(a[2], b[1]));
+  r[1] = xadd(xadd(xsub(xmul(a[3], b[1]), xmul(a[0], b[2])), xmul(a[1], b[3])), xmul(a[2], b[0]));
+  r[2] = xadd(xsub(xadd(xmul(a[3], b[2]), xmul(a[0], b[1])), xmul(a[1], b[0])), xmul(a[2], b[3]));
+}
+
+__global__ void k_icp_init(IcpState* st, const float* init7_src, float t0, float t1, float t2,
+                           float q0, float q1, float q2, float q3) {
+  (void)init7_src;
+  st->T[0] = t0;
+  st->T[1] = t1;
+  st->T[2] = t2;
+  st->T[3] = q0;
+  st->T[4] = q1;
+  st->T[5] = q2;
+  st->T[6] = q3;
+  st->prev_mse = INFINITY;
+  st->mse = INFINITY;
+  st->iterations = 0;
+  st->converged = 0;
+  st->status = 0;
+  st->done = 0;
+  st->ticket = 0;
+  st->n_valid = 0.0;
+}
+
+__global__ void __launch_bounds__(kIcpBlock)
+k_gather_normals(const float* __restrict__ nrm, const float4* __restrict__ pts, uint32_t n,
+                 float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t j = __float_as_uint(__ldg(&pts[i]).w);
+    const float* p = nrm + 3 * (uint64_t)j;
+    out[i] = make_float4(p[0], p[1], p[2], 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(kIcpBlock)
+k_icp_correspond(GridParams g, const float4* __restrict__ tgt, const uint32_t* __restrict__ cell_start,
+                 const float4* __restrict__ tgt_nrm, const float4* __restrict__ src, uint32_t ns,
+                 float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
+                 double* __restrict__ sums, uint32_t* __restrict__ match_out) {
+  if (st->done) return;
+  float T[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T[i] = st->T[i];
+  double acc[kNumSums];
+#pragma unroll
+  for (int i = 0; i < kNumSums; ++i) acc[i] = 0.0;
+
+  for (uint32_t i = blockIdx.x * kIcpBlock + threadIdx.x; i < ns; i += gridDim.x * kIcpBlock) {
+    const float4 s4 = __ldg(&src[i]);
+    // current_transform * p  (registration.rs:540-544)
+    V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
+    s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
+    Best1 best;
+    grid_search(g, tgt, cell_start, s.x, s.y, s.z, best);
+    bool valid = best.full();
+    if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
+      if (xsqrt(best.kth()) > max_dist) valid = false;
+    }
+    if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
+    if (valid) {
+      const float4 d4 = __ldg(&tgt[best.pos]);
+      const float4 n4 = __ldg(&tgt_nrm[best.pos]);
+      const V3 n{n4.x, n4.y, n4.z};
+      const V3 c = xcross(s, n);  // registration.rs:418
+      const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
+      const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
+      const double a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
+      const double bd = b;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc) acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += a[r] * a[cc];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * bd;
+      acc[27] += bd * bd;
+      acc[28] += 1.0;
+    }
+  }
+  // warp-shuffle tree, then one row per warp in shared memory
+  __shared__ double sm[kIcpBlock / 32][kNumSums];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kNumSums; ++i) {
+    double v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kIcpBlock / 32; ++w) v += sm[w][threadIdx.x];
+    partials[(uint64_t)blockIdx.x * kNumSums + threadIdx.x] = v;
+  }
+  __threadfence();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < kNumSums) {
+      double v = 0.0;
+      for (uint32_t b = 0; b < gridDim.x; ++b)
+        v += __ldcg(&partials[(uint64_t)b * kNumSums + threadIdx.x]);
+      sums[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) st->ticket = 0;
+  }
+}
+
+// 6x6 SPD solve in f64: Cholesky, falling back to LU with partial pivoting
+// (registration.rs:432-438).  Returns 0 ok, 1 singular.
+__device__ int solve6(const double* s /*21 upper-tri row-major*/, const double* rhs, double x[6]) {
+  double A[6][6];
+  int t = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) {
+      A[r][c] = s[t];
+      A[c][r] = s[t];
+      ++t;
+    }
+  double L[6][6];
+  bool ok = true;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) L[r][c] = A[r][c];
+  for (int j = 0; j < 6 && ok; ++j) {
+    for (int k = 0; k < j; ++k) {
+      const double f = L[j][k];
+      for (int r = j; r < 6; ++r) L[r][j] -= f * L[r][k];
+    }
+    const double d = L[j][j];
+    if (!(d > 0.0)) {
+      ok = false;
+      break;
+    }
+    const double sd = sqrt(d);
+    L[j][j] = sd;
+    for (int r = j + 1; r < 6; ++r) L[r][j] /= sd;
+  }
+  if (ok) {
+    for (int i = 0; i < 6; ++i) x[i] = rhs[i];
+    for (int i = 0; i < 6; ++i) {
+      x[i] /= L[i][i];
+      for (int r = i + 1; r < 6; ++r) x[r] -= x[i] * L[r][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double d = 0.0;
+      for (int r = i + 1; r < 6; ++r) d += L[r][i] * x[r];
+      x[i] = (x[i] - d) / L[i][i];
+    }
+    return 0;
+  }
+  // LU with partial pivoting
+  double b[6];
+  for (int i = 0; i < 6; ++i) b[i] = rhs[i];
+  for (int i = 0; i < 6; ++i) {
+    int piv = i;
+    double best = fabs(A[i][i]);
+    for (int r = i + 1; r < 6; ++r)
+      if (fabs(A[r][i]) > best) {
+        best = fabs(A[r][i]);
+        piv = r;
+      }
+    if (A[piv][i] == 0.0 || !isfinite(A[piv][i])) return 1;
+    if (piv != i) {
+      for (int c = 0; c < 6; ++c) {
+        const double tmp = A[i][c];
+        A[i][c] = A[piv][c];
+        A[piv][c] = tmp;
+      }
+      const double tb = b[i];
+      b[i] = b[piv];
+      b[piv] = tb;
+    }
+    for (int r = i + 1; r < 6; ++r) {
+      const double f = A[r][i] / A[i][i];
+      for (int c = i + 1; c < 6; ++c) A[r][c] -= f * A[i][c];
+      b[r] -= f * b[i];
+    }
+  }
+  for (int i = 5; i >= 0; --i) {
+    for (int c = i + 1; c < 6; ++c) b[i] -= A[i][c] * b[c];
+    b[i] /= A[i][i];
+    x[i] = b[i];
+  }
+  return 0;
+}
+
+__global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ sums, float conv) {
+  if (threadIdx.x != 0 || st->done) return;
+  const double n_valid = sums[28];
+  st->n_valid = n_valid;
+  if (n_valid < 6.0) {  // registration.rs:568-572
+    st->status = 2;
+    st->done = 1;
+    return;
+  }
+  double x[6];
+  if (solve6(sums, sums + 21, x) != 0) {  // registration.rs:435-437
+    st->status = 3;
+    st->done = 1;
+    return;
+  }
+  // delta = (Rz * Ry * Rx, t)  (registration.rs:441-449), quaternions as from_axis_angle
+  const float ax = (float)x[0], ay = (float)x[1], az = (float)x[2];
+  float sx, cx, sy, cy, sz, cz;
+  sincosf(xdiv(ax, 2.0f), &sx, &cx);
+  sincosf(xdiv(ay, 2.0f), &sy, &cy);
+  sincosf(xdiv(az, 2.0f), &sz, &cz);
+  const float qx[4] = {sx, 0.0f, 0.0f, cx};
+  const float qy[4] = {0.0f, sy, 0.0f, cy};
+  const float qz[4] = {0.0f, 0.0f, sz, cz};
+  float qzy[4], dq[4];
+  quat_mul(qz, qy, qzy);
+  quat_mul(qzy, qx, dq);
+  const float dt[3] = {(float)x[3], (float)x[4], (float)x[5]};
+  // T <- delta * T = (dq * q, dt + dq . t)   (registration.rs:576)  [nalgebra Isometry3 product]
+  float q_old[4] = {st->T[3], st->T[4], st->T[5], st->T[6]};
+  const V3 sh = quat_rotate(dq, V3{st->T[0], st->T[1], st->T[2]});
+  float qn[4];
+  quat_mul(dq, q_old, qn);
+  st->T[0] = xadd(dt[0], sh.x);
+  st->T[1] = xadd(dt[1], sh.y);
+  st->T[2] = xadd(dt[2], sh.z);
+  st->T[3] = qn[0];
+  st->T[4] = qn[1];
+  st->T[5] = qn[2];
+  st->T[6] = qn[3];
+  // mean b^2 over valid pairs, residuals taken BEFORE delta (registration.rs:453-471, 578)
+  const float mse = (float)(sums[27] / n_valid);
+  st->iterations += 1;
+  st->mse = mse;
+  if (fabsf(st->prev_mse - mse) < conv) {  // registration.rs:579-589
+    st->converged = 1;
+    st->done = 1;
+    return;
+  }
+  st->prev_mse = mse;
+}
+
+}  // namespace
+
+extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                                            const tc_index* tgt, const float* d_tgt_normals_aos,
+                                            const float init[7], uint32_t max_iters,
+                                            float max_corr_dist, float conv_threshold,
+                                            tc_icp_result* out, uint32_t* d_match_out) {
+  if (!ctx || !src || !tgt || !out || !init) return TC_INVALID_DATA;
+  // validation order of registration.rs:517-531 (normals length is checked by the host wrapper)
+  if ((src->n == 0 && !comm) || tgt->n == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
+  if (!d_tgt_normals_aos)
+    return tc_fail(ctx, TC_INVALID_DATA,
+                   "target_normals length must equal the number of target points");
+  if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
+  const uint32_t ns = (uint32_t)src->n;
+  const uint32_t nt = (uint32_t)tgt->n;
+
+  // sort the source spatially (own bbox, target-sized cells) so warps walk coherent target cells
+  float4* d_src = nullptr;
+  if (ns > 0) {
+    float mn[3], mx[3];
+    TC_TRY(tci_bbox(ctx, src->d_xyz, ns, mn, mx));
+    GridParams sg{};
+    sg.ox = mn[0];
+    sg.oy = mn[1];
+    sg.oz = mn[2];
+    float cell = tgt->g.cell * 2.0f;
+    const float emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    if (!(cell > 0)) cell = 1.0f;
+    if (emax / cell > 1000.0f) cell = emax / 1000.0f;  // <= ~2^30 cells
+    sg.cell = cell;
+    sg.inv = 1.0f / cell;
+    sg.nx = (int)std::floor((mx[0] - mn[0]) / cell) + 1;
+    sg.ny = (int)std::floor((mx[1] - mn[1]) / cell) + 1;
+    sg.nz = (int)std::floor((mx[2] - mn[2]) / cell) + 1;
+    sg.n = ns;
+    TC_TRY(tci_sort_by_grid(ctx, src->d_xyz, ns, sg, &d_src));
+  }
+  const int grid = std::max(1, std::min((int)((ns + kIcpBlock - 1) / kIcpBlock), ctx->sm_count * 4));
+
+  float4* d_nrm = nullptr;
+  IcpState* d_state = nullptr;
+  double *d_partials = nullptr, *d_sums = nullptr;
+  int st = tc_alloc(ctx, &d_nrm, nt);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_state, 1);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_partials, (uint64_t)grid * kNumSums);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_sums, kNumSums);
+  IcpState h_state{};
+  if (st == TC_OK) {
+    k_gather_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
+                                            ctx->sm_count * 8)),
+                       kIcpBlock, 0, ctx->stream>>>(d_tgt_normals_aos, tgt->d_pts, nt, d_nrm);
+    ctx->launches++;
+    k_icp_init<<<1, 1, 0, ctx->stream>>>(d_state, nullptr, init[0], init[1], init[2], init[3],
+                                         init[4], init[5], init[6]);
+    ctx->launches++;
+    for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
+      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(tgt->g, tgt->d_pts, tgt->d_cell_start,
+                                                            d_nrm, d_src, ns, max_corr_dist,
+                                                            d_state, d_partials, d_sums,
+                                                            d_match_out);
+      ctx->launches++;
+      if (comm) st = tci_comm_allreduce(comm, d_sums, kNumSums);
+      k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
+      ctx->launches++;
+    }
+    if (st == TC_OK && cudaGetLastError() != cudaSuccess)
+      st = tc_fail(ctx, TC_GPU, "ICP kernel launch failed");
+    if (st == TC_OK) {
+      cudaError_t e = cudaMemcpyAsync(&h_state, d_state, sizeof(IcpState), cudaMemcpyDeviceToHost,
+                                      ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess)
+        st = tc_fail(ctx, TC_GPU, std::string("ICP failed: ") + cudaGetErrorString(e));
+    }
+  }
+  tc_free(ctx, d_src);
+  tc_free(ctx, d_nrm);
+  tc_free(ctx, d_state);
+  tc_free(ctx, d_partials);
+  tc_free(ctx, d_sums);
+  if (st != TC_OK) return st;
+  if (h_state.status == 2)
+    return tc_fail(ctx, TC_ALGORITHM,
+                   "Insufficient correspondences for point-to-plane ICP (need >= 6)");
+  if (h_state.status == 3)
+    return tc_fail(ctx, TC_ALGORITHM, "Point-to-plane system is ill-conditioned");
+  for (int i = 0; i < 7; ++i) out->transform[i] = h_state.T[i];
+  // converged: current mse, iteration+1; otherwise previous_mse (== last mse), max_iters
+  out->mse = h_state.converged ? h_state.mse : h_state.prev_mse;
+  out->iterations = h_state.iterations;
+  out->converged = h_state.converged;
+  out->n_correspondences = (uint64_t)h_state.n_valid;
+  return TC_OK;
+}

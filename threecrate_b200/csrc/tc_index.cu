@@ -1,0 +1,586 @@
+// tc_index.cu — device-resident uniform-grid index: bbox -> cell keys -> LSD radix sort ->
+// cell-range scan -> sorted float4 points.  Replaces KdTree::new
+// (threecrate-algorithms/src/nearest_neighbor.rs:37-159), which is a serial O(N log N) quickselect.
+//
+// All kernels are HBM-bound streaming passes (coalesced loads, grid sized in multiples of the SM
+// count).  Algorithmic bytes per point: bbox 12, keys+histogram 12r+4w, radix passes
+// (8r+8w) x P with P = ceil(key_bits/8), gather 4r+12r+16w, cell-range scan 8 B/cell.
+#include "tc_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(tc_context* ctx, uint64_t n, int per_block, int waves = 8) {
+  uint64_t blocks = (n + per_block - 1) / per_block;
+  uint64_t cap = (uint64_t)ctx->sm_count * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------- bbox
+__global__ void k_scratch_init(uint32_t* s) {
+  const int t = threadIdx.x;
+  if (t < 3) s[t] = 0xFFFFFFFFu;       // min (ordered encoding)
+  else if (t < 6) s[t] = 0u;           // max
+  else if (t < 64) s[t] = 0u;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz, uint64_t n,
+                                                   uint32_t* __restrict__ s) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  uint32_t bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = xyz[3 * i + a];
+      if (!isfinite(v)) bad = 1;
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (mn[a] <= mx[a]) {
+        atomicMin(&s[a], f2ord(mn[a]));
+        atomicMax(&s[3 + a], f2ord(mx[a]));
+      }
+    }
+    if (bad) atomicOr(&s[6], 1u);
+  }
+}
+
+// ------------------------------------------------------------------- cell keys + histogram
+// MODE 0: keys + histogram (index build).  MODE 1: keys only (spatial sort of queries).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict__ xyz, uint32_t n,
+                                                        GridParams g, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ counts) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float u;
+    const int cx = cell_coord(xyz[3 * (uint64_t)i + 0], g.ox, g.inv, g.nx, u);
+    const int cy = cell_coord(xyz[3 * (uint64_t)i + 1], g.oy, g.inv, g.ny, u);
+    const int cz = cell_coord(xyz[3 * (uint64_t)i + 2], g.oz, g.inv, g.nz, u);
+    const uint32_t c = cell_id(g, cx, cy, cz);
+    keys[i] = c;
+    if (MODE == 0) atomicAdd(&counts[c], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
+                                                         uint64_t n_cells,
+                                                         uint32_t* __restrict__ s) {
+  uint32_t occ = 0, mx = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = counts[i];
+    occ += (c != 0);
+    mx = max(mx, c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    occ += __shfl_xor_sync(0xffffffffu, occ, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (occ) atomicAdd(&s[8], occ);
+    if (mx) atomicMax(&s[9], mx);
+  }
+}
+
+// ---------------------------------------------------------------------- exclusive scan (u32)
+// reduce-then-scan: tile sums -> scan of tile sums (one block) -> per-tile exclusive scan.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp,
+                                                         uint32_t& total) {
+  // returns exclusive prefix of v across the block (kScanThreads threads), total = block sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) smem_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (kScanThreads / 32) ? smem_warp[lane] : 0;
+    uint32_t wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < (kScanThreads / 32)) smem_warp[lane] = wi - w;  // exclusive warp offsets
+    if (lane == (kScanThreads / 32) - 1) smem_warp[kScanThreads / 32] = wi;
+  }
+  __syncthreads();
+  total = smem_warp[kScanThreads / 32];
+  const uint32_t res = smem_warp[warp] + incl - v;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const uint32_t* __restrict__ in,
+                                                                 uint64_t n,
+                                                                 uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t sw[kScanThreads / 32 + 1];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int it = 0; it < kScanItems; ++it) {
+    const uint64_t i = base + (uint64_t)it * kScanThreads + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  uint32_t total;
+  block_exclusive_scan(s, sw, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint32_t* __restrict__ tile_sums,
+                                                            uint32_t n_tiles) {
+  __shared__ uint32_t sw[kScanThreads / 32 + 1];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n_tiles; base += kScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, sw, total);
+    if (i < n_tiles) tile_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+// out[i] = exclusive prefix; additionally out[n] = grand total (out has n + 1 entries).
+__global__ void __launch_bounds__(kScanThreads) k_scan_final(const uint32_t* __restrict__ in,
+                                                             uint64_t n,
+                                                             const uint32_t* __restrict__ tile_offs,
+                                                             uint32_t* __restrict__ out) {
+  __shared__ uint32_t sw[kScanThreads / 32 + 1];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int it = 0; it < kScanItems; ++it) {
+    const uint64_t i = base + it;
+    v[it] = i < n ? in[i] : 0;
+    s += v[it];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, sw, total) + tile_offs[blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < kScanItems; ++it) {
+    const uint64_t i = base + it;
+    if (i < n) out[i] = ex;
+    ex += v[it];
+    if (i == n - 1) out[n] = ex;
+  }
+}
+
+// ------------------------------------------------------------------------- LSD radix sort
+// 8-bit digits; per pass: tile histogram -> exclusive scan of hist[digit][tile] -> stable scatter.
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 keys per block
+constexpr int kRsWarps = kRsThreads / 32;
+
+__global__ void __launch_bounds__(kRsThreads) k_radix_hist(const uint32_t* __restrict__ keys,
+                                                           uint32_t n, int shift,
+                                                           uint32_t* __restrict__ hist,
+                                                           uint32_t n_tiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kRsTile;
+#pragma unroll
+  for (int it = 0; it < kRsItems; ++it) {
+    const uint64_t i = base + (uint64_t)it * kRsThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// vals_in == nullptr means the identity permutation (first pass).
+__global__ void __launch_bounds__(kRsThreads)
+k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                int shift, const uint32_t* __restrict__ offs, uint32_t n_tiles) {
+  __shared__ uint32_t whist[kRsWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) ((uint32_t*)whist)[i] = 0;
+  __syncthreads();
+  // tile element order: warp-major, then round, then lane  (== global order)
+  const uint64_t base = (uint64_t)blockIdx.x * kRsTile + (uint64_t)warp * (32 * kRsItems);
+  uint32_t key[kRsItems], rank[kRsItems];
+#pragma unroll
+  for (int it = 0; it < kRsItems; ++it) {
+    const uint64_t i = base + it * 32 + lane;
+    const bool valid = i < n;
+    key[it] = valid ? keys_in[i] : 0xFFFFFFFFu;
+    const uint32_t digit = (key[it] >> shift) & 255u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (0x100u | lane));
+    const int leader = __ffs(peers) - 1;
+    uint32_t pre = 0;
+    if (lane == leader && valid) {
+      pre = whist[warp][digit];
+      whist[warp][digit] = pre + __popc(peers);
+    }
+    pre = __shfl_sync(0xffffffffu, pre, leader);
+    rank[it] = pre + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;
+    uint32_t run = offs[(uint64_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) {
+      const uint32_t c = whist[w][d];
+      whist[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kRsItems; ++it) {
+    const uint64_t i = base + it * 32 + lane;
+    if (i < n) {
+      const uint32_t digit = (key[it] >> shift) & 255u;
+      const uint32_t pos = whist[warp][digit] + rank[it];
+      keys_out[pos] = key[it];
+      vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- gather
+__global__ void __launch_bounds__(kThreads) k_gather(const float* __restrict__ xyz,
+                                                     const uint32_t* __restrict__ perm, uint32_t n,
+                                                     float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t j = perm[i];
+    const float* p = xyz + 3 * (uint64_t)j;
+    out[i] = make_float4(p[0], p[1], p[2], __uint_as_float(j));
+  }
+}
+
+int key_bits_for(uint64_t n_cells) {
+  int b = 1;
+  while (b < 32 && (1ull << b) < n_cells) ++b;
+  return b;
+}
+
+}  // namespace
+
+// ==========================================================================================
+int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n) {
+  if (n == 0) {
+    TC_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(uint32_t), ctx->stream));
+    return TC_OK;
+  }
+  const uint32_t n_tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  uint32_t* d_sums = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_sums, n_tiles));
+  k_scan_tile_sums<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_sums);
+  TC_LAUNCHED(ctx);
+  k_scan_sums<<<1, kScanThreads, 0, ctx->stream>>>(d_sums, n_tiles);
+  TC_LAUNCHED(ctx);
+  k_scan_final<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_sums, d_out);
+  TC_LAUNCHED(ctx);
+  tc_free(ctx, d_sums);
+  return TC_OK;
+}
+
+int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_alt,
+                         uint32_t* d_vals_alt, uint32_t n, int key_bits, uint32_t** keys_out,
+                         uint32_t** vals_out) {
+  // d_vals may be nullptr on entry => identity values; the result then lands in the alt buffers
+  // or (d_keys, d_vals_alt2) — to keep it simple the caller always provides both value buffers.
+  const uint32_t n_tiles = (n + kRsTile - 1) / kRsTile;
+  uint32_t* d_hist = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_hist, (uint64_t)256 * n_tiles + 1));
+  uint32_t *kin = d_keys, *kout = d_keys_alt, *vin = nullptr, *vout = d_vals_alt;
+  uint32_t* vother = d_vals;
+  const int passes = (key_bits + 7) / 8;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    k_radix_hist<<<n_tiles, kRsThreads, 0, ctx->stream>>>(kin, n, shift, d_hist, n_tiles);
+    TC_LAUNCHED(ctx);
+    TC_TRY(tci_exclusive_scan_u32(ctx, d_hist, d_hist, (uint64_t)256 * n_tiles));
+    k_radix_scatter<<<n_tiles, kRsThreads, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, d_hist,
+                                                             n_tiles);
+    TC_LAUNCHED(ctx);
+    // ping-pong
+    uint32_t* t = kin;
+    kin = kout;
+    kout = t;
+    vin = vout;
+    vout = vother;
+    vother = vin;
+  }
+  tc_free(ctx, d_hist);
+  *keys_out = kin;
+  *vals_out = vin;
+  return TC_OK;
+}
+
+int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]) {
+  k_scratch_init<<<1, 64, 0, ctx->stream>>>(ctx->d_scratch);
+  TC_LAUNCHED(ctx);
+  k_bbox<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(d_xyz, n, ctx->d_scratch);
+  TC_LAUNCHED(ctx);
+  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_scratch[6] != 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "point coordinates must be finite (NaN/Inf found)");
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = ord2f(ctx->h_scratch[a]);
+    mx[a] = ord2f(ctx->h_scratch[3 + a]);
+  }
+  return TC_OK;
+}
+
+namespace {
+
+constexpr uint64_t kMaxCells = 1ull << 27;
+
+// dims for a given cell size, shrinking resolution if the table would be too large
+GridParams make_grid(const float mn[3], const float mx[3], float cell, uint64_t n,
+                     uint64_t max_cells) {
+  GridParams g{};
+  g.ox = mn[0];
+  g.oy = mn[1];
+  g.oz = mn[2];
+  g.ex = mx[0] - mn[0];
+  g.ey = mx[1] - mn[1];
+  g.ez = mx[2] - mn[2];
+  g.n = (uint32_t)n;
+  for (int attempt = 0; attempt < 64; ++attempt) {
+    const double dx = std::floor((double)g.ex / cell) + 1, dy = std::floor((double)g.ey / cell) + 1,
+                 dz = std::floor((double)g.ez / cell) + 1;
+    if (dx * dy * dz <= (double)max_cells && dx < 2e9 && dy < 2e9 && dz < 2e9) {
+      g.nx = (int)dx;
+      g.ny = (int)dy;
+      g.nz = (int)dz;
+      break;
+    }
+    cell *= 1.26f;  // ~2x fewer cells per step
+  }
+  if (g.nx < 1) g.nx = g.ny = g.nz = 1;
+  g.cell = cell;
+  g.inv = 1.0f / cell;
+  return g;
+}
+
+float target_population(uint32_t k_hint) {
+  // points per occupied cell aimed for: ring-1 (3x3x3) search is exact when the k-th neighbour
+  // lies within one cell edge; ~0.55 (k+1) per cell keeps that true for surface-like data.
+  float t = 0.55f * (float)(k_hint + 1);
+  if (t < 2.0f) t = 2.0f;
+  if (t > 48.0f) t = 48.0f;
+  return t;
+}
+
+}  // namespace
+
+extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint,
+                              float cell_size, tc_index** out) {
+  if (!ctx || !cloud || !out) return TC_INVALID_DATA;
+  *out = nullptr;
+  const uint64_t n = cloud->n;
+  if (n >= 0xFFFFFFFFull) return tc_fail(ctx, TC_INVALID_DATA, "cloud too large (N must be < 2^32-1)");
+  tc_index* ix = new tc_index();
+  ix->ctx = ctx;
+  ix->cloud = cloud;
+  ix->n = n;
+  if (n == 0) {
+    ix->g.nx = ix->g.ny = ix->g.nz = 1;
+    ix->g.cell = 1.0f;
+    ix->g.inv = 1.0f;
+    ix->n_cells = 1;
+    *out = ix;
+    return TC_OK;
+  }
+  int st = tci_bbox(ctx, cloud->d_xyz, n, ix->bbox_min, ix->bbox_max);
+  if (st != TC_OK) {
+    delete ix;
+    return st;
+  }
+  const float* mn = ix->bbox_min;
+  const float* mx = ix->bbox_max;
+  const double ex = (double)mx[0] - mn[0], ey = (double)mx[1] - mn[1], ez = (double)mx[2] - mn[2];
+  const double emax = std::max(ex, std::max(ey, ez));
+
+  uint32_t* d_keys = nullptr;
+  uint32_t* d_counts = nullptr;
+  st = tc_alloc(ctx, &d_keys, n);
+  if (st != TC_OK) {
+    delete ix;
+    return st;
+  }
+  const uint64_t table_cap = std::min<uint64_t>(kMaxCells, std::max<uint64_t>(8 * n, 1u << 16));
+
+  float cell = cell_size;
+  const bool auto_cell = !(cell_size > 0.0f);
+  if (auto_cell) {
+    // first guess: surface-like data, area proxy = sum of the three bbox face areas
+    const float target = target_population(k_hint);
+    double area = ex * ey + ey * ez + ex * ez;
+    if (area <= 0) area = emax * emax;
+    if (area <= 0) area = 1.0;
+    cell = (float)std::sqrt(target * area / (double)n);
+    if (!(cell > 0) || !std::isfinite(cell)) cell = 1.0f;
+    if (emax > 0 && cell > emax) cell = (float)emax;
+    if (emax > 0 && cell < emax * 1e-6) cell = (float)(emax * 1e-6);
+  }
+  GridParams g{};
+  const int max_trials = auto_cell ? 4 : 1;
+  for (int trial = 0; trial < max_trials; ++trial) {
+    g = make_grid(mn, mx, cell, n, table_cap);
+    cell = g.cell;
+    const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
+    tc_free(ctx, d_counts);
+    st = tc_alloc(ctx, &d_counts, n_cells + 1);
+    if (st != TC_OK) break;
+    cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream);
+    k_cell_keys<0><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
+        cloud->d_xyz, (uint32_t)n, g, d_keys, d_counts);
+    ctx->launches++;
+    cudaMemsetAsync(ctx->d_scratch + 8, 0, 2 * sizeof(uint32_t), ctx->stream);
+    k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
+        d_counts, n_cells, ctx->d_scratch);
+    ctx->launches++;
+    cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 2 * sizeof(uint32_t),
+                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      st = tc_fail(ctx, TC_GPU, "index build: histogram pass failed");
+      break;
+    }
+    ix->occupied = ctx->h_scratch[8];
+    ix->max_pop = ctx->h_scratch[9];
+    if (!auto_cell || trial == max_trials - 1) break;
+    const float target = target_population(k_hint);
+    const float pop = (float)n / (float)std::max(1u, ix->occupied);
+    if (pop > target * 0.7f && pop < target * 1.4f) break;
+    // rescale assuming surface-like scaling (occupied cells ~ cell^-2); clamp the step
+    float scale = std::sqrt(target / pop);
+    scale = std::min(4.0f, std::max(0.25f, scale));
+    float next = cell * scale;
+    if (emax > 0 && next > emax) next = (float)emax;
+    if (std::fabs(next - cell) < 1e-3f * cell) break;
+    // cannot refine beyond the table capacity
+    GridParams probe = make_grid(mn, mx, next, n, table_cap);
+    if (probe.cell == cell) break;
+    cell = next;
+  }
+  if (st != TC_OK) {
+    tc_free(ctx, d_keys);
+    tc_free(ctx, d_counts);
+    delete ix;
+    return st;
+  }
+  ix->g = g;
+  ix->n_cells = (uint64_t)g.nx * g.ny * g.nz;
+
+  // cell-range scan: counts -> cell_start (n_cells + 1 entries)
+  st = tc_alloc(ctx, &ix->d_cell_start, ix->n_cells + 1);
+  if (st == TC_OK) st = tci_exclusive_scan_u32(ctx, d_counts, ix->d_cell_start, ix->n_cells);
+  tc_free(ctx, d_counts);
+
+  // radix sort (key, original index) and gather into sorted float4
+  uint32_t *d_keys_alt = nullptr, *d_vals = nullptr, *d_vals_alt = nullptr;
+  uint32_t *ks = nullptr, *vs = nullptr;
+  if (st == TC_OK) st = tc_alloc(ctx, &d_keys_alt, n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_vals, n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_vals_alt, n);
+  if (st == TC_OK)
+    st = tci_radix_sort_pairs(ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n,
+                              key_bits_for(ix->n_cells), &ks, &vs);
+  if (st == TC_OK) st = tc_alloc(ctx, &ix->d_pts, n);
+  if (st == TC_OK) {
+    k_gather<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, vs, (uint32_t)n,
+                                                                       ix->d_pts);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "gather launch failed");
+  }
+  tc_free(ctx, d_keys);
+  tc_free(ctx, d_keys_alt);
+  tc_free(ctx, d_vals);
+  tc_free(ctx, d_vals_alt);
+  if (st != TC_OK) {
+    tc_index_free(ix);
+    return st;
+  }
+  *out = ix;
+  return TC_OK;
+}
+
+extern "C" void tc_index_free(tc_index* ix) {
+  if (!ix) return;
+  tc_free(ix->ctx, ix->d_pts);
+  tc_free(ix->ctx, ix->d_cell_start);
+  delete ix;
+}
+
+extern "C" int tc_index_get_info(const tc_index* ix, tc_index_info* out) {
+  if (!ix || !out) return TC_INVALID_DATA;
+  out->n_points = ix->n;
+  out->n_cells = ix->n_cells;
+  out->dims[0] = ix->g.nx;
+  out->dims[1] = ix->g.ny;
+  out->dims[2] = ix->g.nz;
+  out->cell_size = ix->g.cell;
+  for (int a = 0; a < 3; ++a) {
+    out->bbox_min[a] = ix->bbox_min[a];
+    out->bbox_max[a] = ix->bbox_max[a];
+  }
+  out->occupied_cells = ix->occupied;
+  out->max_cell_population = ix->max_pop;
+  return TC_OK;
+}
+
+// Sort arbitrary points (queries / ICP source) by the cells of grid g so that neighbouring
+// threads walk neighbouring cells.  Key = clamped cell id in g.
+int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const GridParams& g,
+                     float4** d_sorted) {
+  *d_sorted = nullptr;
+  if (n == 0) return TC_OK;
+  uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_vals = nullptr, *d_vals_alt = nullptr;
+  uint32_t *ks = nullptr, *vs = nullptr;
+  int st = tc_alloc(ctx, &d_keys, n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_keys_alt, n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_vals, n);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_vals_alt, n);
+  if (st == TC_OK) {
+    k_cell_keys<1><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(d_xyz, (uint32_t)n, g,
+                                                                            d_keys, nullptr);
+    ctx->launches++;
+    const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
+    st = tci_radix_sort_pairs(ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n,
+                              key_bits_for(n_cells), &ks, &vs);
+  }
+  if (st == TC_OK) st = tc_alloc(ctx, d_sorted, n);
+  if (st == TC_OK) {
+    k_gather<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(d_xyz, vs, (uint32_t)n,
+                                                                       *d_sorted);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "gather launch failed");
+  }
+  tc_free(ctx, d_keys);
+  tc_free(ctx, d_keys_alt);
+  tc_free(ctx, d_vals);
+  tc_free(ctx, d_vals_alt);
+  return st;
+}

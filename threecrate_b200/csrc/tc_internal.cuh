@@ -1,0 +1,162 @@
+// tc_internal.cuh — shared declarations of the threecrate_cuda library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+
+#include "../../include/threecrate_cuda.h"
+
+// ------------------------------------------------------------------------------------------
+// host-side objects behind the opaque handles
+// ------------------------------------------------------------------------------------------
+struct tc_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // small device scratch (bbox / stats / flags) and its pinned host mirror
+  uint32_t* d_scratch = nullptr;   // 64 words
+  uint32_t* h_scratch = nullptr;   // pinned, 64 words
+};
+
+struct tc_cloud {
+  tc_context* ctx = nullptr;
+  uint64_t n = 0;
+  float* d_xyz = nullptr;  // n x 3 AoS, original order
+};
+
+// Grid geometry, passed to kernels by value.
+struct GridParams {
+  float ox, oy, oz;     // origin = bbox min
+  float inv;            // 1 / cell (the f32 value actually used for cell assignment)
+  float cell;           // cell edge
+  float ex, ey, ez;     // bbox extents (for the conservative ring bound)
+  int nx, ny, nz;
+  uint32_t n;           // points in the index
+};
+
+struct tc_index {
+  tc_context* ctx = nullptr;
+  const tc_cloud* cloud = nullptr;  // borrowed; must outlive the index
+  uint64_t n = 0;
+  GridParams g{};
+  float bbox_min[3]{}, bbox_max[3]{};
+  uint64_t n_cells = 0;
+  float4* d_pts = nullptr;          // sorted by cell: x, y, z, bits(original index)
+  uint32_t* d_cell_start = nullptr; // n_cells + 1
+  uint32_t occupied = 0, max_pop = 0;
+};
+
+struct tc_comm;  // tc_comm.cu
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+inline int tc_fail(tc_context* ctx, int status, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+#define TC_CUDA(ctx, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return tc_fail((ctx), TC_GPU,                                                         \
+                     std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                         ":" + std::to_string(__LINE__) + ")");                             \
+  } while (0)
+#define TC_TRY(expr)               \
+  do {                             \
+    int s__ = (expr);              \
+    if (s__ != TC_OK) return s__;  \
+  } while (0)
+// count + check a kernel launch
+#define TC_LAUNCHED(ctx)                         \
+  do {                                           \
+    (ctx)->launches++;                           \
+    TC_CUDA((ctx), cudaGetLastError());          \
+  } while (0)
+
+// stream-ordered allocation from the device's default pool (cached across calls)
+template <typename T>
+inline int tc_alloc(tc_context* ctx, T** p, uint64_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  TC_CUDA(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+  return TC_OK;
+}
+inline void tc_free(tc_context* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// internal entry points shared between translation units
+// ------------------------------------------------------------------------------------------
+// tc_index.cu
+int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]);
+// Spatially sort arbitrary points by the cells of grid `g` (clamped): returns float4
+// (x,y,z,bits(orig idx)) in *d_sorted (caller frees with tc_free).
+int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const GridParams& g,
+                     float4** d_sorted);
+int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_alt,
+                         uint32_t* d_vals_alt, uint32_t n, int key_bits, uint32_t** keys_out,
+                         uint32_t** vals_out);
+int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
+
+// tc_search.cu
+int tci_knn_launch(tc_context* ctx, const tc_index* index, const float4* d_queries_sorted,
+                   uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
+                   uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out);
+int tci_normals_launch(tc_context* ctx, const tc_index* index, uint32_t k, int orient,
+                       const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos);
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// Exact (unfused, round-to-nearest) f32 ops: Rust never contracts a*b+c into an FMA, so the
+// distance / covariance / transform arithmetic must not either.
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+
+// KdTree::distance_squared (nearest_neighbor.rs:162-167): (dx*dx + dy*dy) + dz*dz
+__device__ __forceinline__ float dist2_exact(float px, float py, float pz, float qx, float qy,
+                                             float qz) {
+  const float dx = xsub(px, qx), dy = xsub(py, qy), dz = xsub(pz, qz);
+  return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+}
+
+// order-preserving float <-> uint (for atomicMin/Max on floats)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((uint32_t)(-(int32_t)(u >> 31)) | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(uint32_t o) {
+  const uint32_t u = o ^ (((o >> 31) - 1u) | 0x80000000u);
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// cell coordinate of a coordinate value along one axis; u is also returned (cell units).
+__device__ __forceinline__ int cell_coord(float x, float o, float inv, int n, float& u) {
+  u = xmul(xsub(x, o), inv);
+  int c = __float2int_rd(u);
+  c = max(0, min(n - 1, c));
+  return c;
+}
+__device__ __forceinline__ uint32_t cell_id(const GridParams& g, int cx, int cy, int cz) {
+  return (uint32_t)(((int64_t)cz * g.ny + cy) * g.nx + cx);
+}
+#endif
