@@ -23,12 +23,24 @@ def _compare(got, ref, check_pairs=True):
         assert len(got.correspondences) == len(ref.correspondences)
 
 
+def _compare_sphere(got, ref):
+    """The reference's sphere fixtures are centred on the origin, so s x n ~ 0 and the rotation
+    block of AtA is numerically singular: rotation (and the iteration at which |d mse| crosses
+    1e-6) is decided by rounding noise in the reference itself.  Compare what is determined."""
+    tr = float(np.linalg.norm(got.translation.astype(np.float64) - ref.translation))
+    print(f"ICP sphere fixture: trans_err={tr:.3e} iters={got.iterations}/{ref.iterations} "
+          f"mse={got.mse:.3e}/{ref.mse:.3e}")
+    assert tr <= 1e-4
+    assert got.converged == ref.converged
+    assert abs(got.mse - ref.mse) < 1e-6
+
+
 def test_reference_fixture_identity(orc):
     # registration.rs:1167-1177
     p, n = synth.fibonacci_sphere(50)
     r = tc.icp_point_to_plane(p, p, n, tc.IDENTITY, 20)
     assert r.converged and r.mse < 1e-6
-    _compare(r, orc.icp_point_to_plane(p, p, n, max_iters=20))
+    _compare_sphere(r, orc.icp_point_to_plane(p, p, n, max_iters=20))
 
 
 def test_reference_fixture_translation(orc):
@@ -38,7 +50,7 @@ def test_reference_fixture_translation(orc):
     r = tc.icp_point_to_plane(p, p + shift, n, tc.IDENTITY, 50)
     assert np.linalg.norm(r.translation - shift) < 0.3 and r.mse < 0.1
     ref = orc.icp_point_to_plane(p, p + shift, n, max_iters=50)
-    _compare(r, ref)
+    _compare_sphere(r, ref)
     assert np.array_equal(r.correspondences, ref.correspondences)
 
 
@@ -59,7 +71,7 @@ def test_reference_fixture_max_distance(orc):
     tgt = p + np.array([0.1, 0, 0], np.float32)
     r = tc.icp_point_to_plane_detailed(p, tgt, n, tc.IDENTITY, 30, 5.0, 1e-6)
     assert r.mse < 0.5
-    _compare(r, orc.icp_point_to_plane(p, tgt, n, max_iters=30, max_dist=5.0))
+    _compare_sphere(r, orc.icp_point_to_plane(p, tgt, n, max_iters=30, max_dist=5.0))
 
 
 def test_insufficient_correspondences_is_algorithm_error():
@@ -75,8 +87,8 @@ def test_nonidentity_init_and_not_converged_semantics(orc):
     init = np.concatenate([[0.02, 0.0, -0.01], synth.quat_from_euler(0.0, 0.01, 0.0)]).astype(np.float32)
     r = tc.icp_point_to_plane_detailed(p, tgt, n, init, 7, None, -1.0)  # conv <= 0: never converges
     ref = orc.icp_point_to_plane(p, tgt, n, init=init, max_iters=7, conv=-1.0)
-    assert not r.converged and r.iterations == 7
-    _compare(r, ref)
+    assert not r.converged and r.iterations == 7 and ref.iterations == 7
+    _compare_sphere(r, ref)
 
 
 @pytest.mark.parametrize("copy_variant", [True, False])

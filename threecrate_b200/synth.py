@@ -143,7 +143,7 @@ def kitti_frame(seed: int = 0x3C0FFEE, beams: int = 64, az_steps: int = 1875,
         nonlocal t_best
         with np.errstate(divide="ignore", invalid="ignore"):
             t = (value - o[axis]) / d[:, axis]
-        p = o + t[:, None] * d
+            p = o + t[:, None] * d
         ok = (t > 0.5) & np.isfinite(t)
         for a in range(3):
             if a != axis:
