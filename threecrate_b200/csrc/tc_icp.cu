@@ -355,8 +355,10 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
     k_icp_init<<<1, 1, 0, ctx->stream>>>(d_state, nullptr, init[0], init[1], init[2], init[3],
                                          init[4], init[5], init[6]);
     ctx->launches++;
+    GridParams gp = tgt->g;
+    gp.flags = g_tc_search_flags;
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
-      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(tgt->g, tgt->d_pts, tgt->d_cell_start,
+      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(gp, tgt->d_pts, tgt->d_cell_start,
                                                             d_nrm, d_src, ns, max_corr_dist,
                                                             d_state, d_partials, d_sums,
                                                             d_match_out);

@@ -38,6 +38,7 @@ struct GridParams {
   float ex, ey, ez;     // bbox extents (for the conservative ring bound)
   int nx, ny, nz;
   uint32_t n;           // points in the index
+  int flags;            // search variant bits (see tc_search.cuh)
 };
 
 struct tc_index {
@@ -108,6 +109,7 @@ int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, ui
 int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 
 // tc_search.cu
+extern int g_tc_search_flags;  // default search variant (tc_debug_set_search_flags)
 int tci_knn_launch(tc_context* ctx, const tc_index* index, const float4* d_queries_sorted,
                    uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out);

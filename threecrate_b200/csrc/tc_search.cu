@@ -216,6 +216,9 @@ inline int pick_size(uint32_t need) {
 
 }  // namespace
 
+int g_tc_search_flags = 3;
+extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
+
 #define TC_DISPATCH_K(SZ, CALL)                     \
   switch (SZ) {                                     \
     case 1: { constexpr int KK = 1; CALL; } break;   \
@@ -247,8 +250,10 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
     return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 64 incl. self)");
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
+  GridParams gp = ix->g;
+  gp.flags = g_tc_search_flags;
   TC_DISPATCH_K(sz, (k_knn<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                        ix->g, ix->d_pts, ix->d_cell_start, d_queries_sorted, (uint32_t)q_begin,
+                        gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, (uint32_t)q_begin,
                         (uint32_t)q_end, k, drop_self, d_idx_out, d_dist_out, d_count_out)));
   TC_LAUNCHED(ctx);
   return TC_OK;
@@ -262,8 +267,10 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
     return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 63 for normals)");
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
+  GridParams gp = ix->g;
+  gp.flags = g_tc_search_flags;
   TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                        ix->g, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, (uint32_t)q_begin,
+                        gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, (uint32_t)q_begin,
                         (uint32_t)q_end, k, orient, vp[0], vp[1], vp[2], d_out_aos)));
   TC_LAUNCHED(ctx);
   return TC_OK;

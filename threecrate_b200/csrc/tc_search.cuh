@@ -27,13 +27,39 @@ struct TopK {
   __device__ __forceinline__ float kth() const {
     return __uint_as_float((uint32_t)(key[K - 1] >> 32));
   }
+  // Candidate scan.  flags bit 0 selects the deferred form: pass 1 only evaluates distances and
+  // records, per lane, which of up to 32 candidates beat the current K-th distance (one bit
+  // each); pass 2 walks the set bits and runs the insertion chain.  In the direct form the warp
+  // pays for the chain whenever ANY lane inserts (nearly every candidate); deferred, the chain
+  // runs max-over-lanes(popcount) times per 32 candidates with most lanes active.
   __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
-                                       float qx, float qy, float qz) {
-    for (uint32_t j = lo; j < hi; ++j) {
-      const float4 c = __ldg(&pts[j]);
-      const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
-      const uint64_t k2 = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
-      if (k2 < key[K - 1]) insert(k2);
+                                       float qx, float qy, float qz, int flags) {
+    if (!(flags & 1)) {
+      for (uint32_t j = lo; j < hi; ++j) {
+        const float4 c = __ldg(&pts[j]);
+        const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+        const uint64_t k2 = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+        if (k2 < key[K - 1]) insert(k2);
+      }
+      return;
+    }
+    for (uint32_t base = lo; base < hi; base += 32) {
+      const uint32_t len = min(32u, hi - base);
+      const float tau = full() ? kth() : INFINITY;
+      uint32_t mask = 0;
+      for (uint32_t t = 0; t < len; ++t) {
+        const float4 c = __ldg(&pts[base + t]);
+        const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+        if (d2 <= tau) mask |= (1u << t);  // <=: equal d2 may still win on the index
+      }
+      while (mask) {
+        const uint32_t t = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float4 c = __ldg(&pts[base + t]);
+        const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+        const uint64_t k2 = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+        if (k2 < key[K - 1]) insert(k2);
+      }
     }
   }
 };
@@ -71,7 +97,7 @@ struct Best1 {
   __device__ __forceinline__ bool full() const { return key != kEmpty; }
   __device__ __forceinline__ float kth() const { return __uint_as_float((uint32_t)(key >> 32)); }
   __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
-                                       float qx, float qy, float qz) {
+                                       float qx, float qy, float qz, int) {
     for (uint32_t j = lo; j < hi; ++j) {
       const float4 c = __ldg(&pts[j]);
       const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
@@ -84,12 +110,21 @@ struct Best1 {
   }
 };
 
+// Conservative lower bound (squared) on the distance from the query to any point in row
+// (y, z): per axis the gap, in cell units, between the query and the nearest face of that row.
+__device__ __forceinline__ float row_gap(int d, float f) {
+  // d = row coordinate - query cell coordinate along the axis; f = fractional cell coordinate
+  return d == 0 ? 0.0f : (d < 0 ? (f + (float)(-d - 1)) : ((float)d - f));
+}
+
 // Exact nearest-neighbour search for one query; Acc is TopK<K> or Best1.
+// flags: bit 0 deferred insertion (TopK), bit 1 prune rows that cannot beat the K-th distance.
 template <class Acc>
 __device__ __forceinline__ void grid_search(const GridParams& g, const float4* __restrict__ pts,
                                             const uint32_t* __restrict__ cell_start, float qx,
                                             float qy, float qz, Acc& tk) {
   tk.init();
+  const int flags = g.flags;
   float ux, uy, uz;
   const int cx = cell_coord(qx, g.ox, g.inv, g.nx, ux);
   const int cy = cell_coord(qy, g.oy, g.inv, g.ny, uy);
@@ -98,19 +133,30 @@ __device__ __forceinline__ void grid_search(const GridParams& g, const float4* _
   const float mx = g.ex + fabsf(qx - g.ox), my = g.ey + fabsf(qy - g.oy),
               mz = g.ez + fabsf(qz - g.oz);
 
-  // rings 0 and 1: the 3x3 rows around the query's row, x-range [cx-1, cx+1] (contiguous)
+  auto scan_row = [&](int y, int z, int xa, int xb) {
+    if ((flags & 2) && tk.full()) {
+      const float by = axis_bound(row_gap(y - cy, fy), g.cell, my);
+      const float bz = axis_bound(row_gap(z - cz, fz), g.cell, mz);
+      if ((by * by + bz * bz) * 0.99999f > tk.kth()) return;  // every point here is farther
+    }
+    const uint32_t row = cell_id(g, 0, y, z);
+    const uint32_t lo = __ldg(&cell_start[row + xa]);
+    const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
+    tk.scan(pts, lo, hi, qx, qy, qz, flags);
+  };
+
+  // rings 0 and 1: the 3x3 rows around the query's row, x-range [cx-1, cx+1] (contiguous);
+  // the query's own row goes first so the K-th distance tightens before the others are tested
   {
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    scan_row(cy, cz, x0, x1);
     for (int dz = -1; dz <= 1; ++dz) {
       const int z = cz + dz;
       if (z < 0 || z >= g.nz) continue;
       for (int dy = -1; dy <= 1; ++dy) {
         const int y = cy + dy;
-        if (y < 0 || y >= g.ny) continue;
-        const uint32_t row = cell_id(g, 0, y, z);
-        const uint32_t lo = __ldg(&cell_start[row + x0]);
-        const uint32_t hi = __ldg(&cell_start[row + x1 + 1]);
-        tk.scan(pts, lo, hi, qx, qy, qz);
+        if (y < 0 || y >= g.ny || (dy == 0 && dz == 0)) continue;
+        scan_row(y, z, x0, x1);
       }
     }
   }
@@ -128,28 +174,16 @@ __device__ __forceinline__ void grid_search(const GridParams& g, const float4* _
     const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
     for (int z = zlo; z <= zhi; ++z) {
       for (int y = ylo; y <= yhi; ++y) {
-        const uint32_t row = cell_id(g, 0, y, z);
         const bool outer = (abs(z - cz) == R) || (abs(y - cy) == R);
         if (outer) {
-          const uint32_t lo = __ldg(&cell_start[row + x0]);
-          const uint32_t hi = __ldg(&cell_start[row + x1 + 1]);
-          tk.scan(pts, lo, hi, qx, qy, qz);
+          scan_row(y, z, x0, x1);
         } else {
-          if (cx - R >= 0) {
-            const uint32_t lo = __ldg(&cell_start[row + cx - R]);
-            const uint32_t hi = __ldg(&cell_start[row + cx - R + 1]);
-            tk.scan(pts, lo, hi, qx, qy, qz);
-          }
-          if (cx + R <= g.nx - 1) {
-            const uint32_t lo = __ldg(&cell_start[row + cx + R]);
-            const uint32_t hi = __ldg(&cell_start[row + cx + R + 1]);
-            tk.scan(pts, lo, hi, qx, qy, qz);
-          }
+          if (cx - R >= 0) scan_row(y, z, cx - R, cx - R);
+          if (cx + R <= g.nx - 1) scan_row(y, z, cx + R, cx + R);
         }
       }
     }
   }
 }
-
 
 }  // namespace tcs

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Kernel A/B bench: times the search kernels for each variant-flag setting and checks the outputs
+are bit-identical across variants.  python tools/kbench.py [--flags 0,1,2,3] [--cells a,b,c]"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import threecrate_b200 as tc  # noqa: E402
+from threecrate_b200 import _lib, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--flags", default="0,1,2,3")
+ap.add_argument("--what", default="c2,c4,c3")
+ap.add_argument("--c4n", type=int, default=2_000_000)
+ap.add_argument("--cellscale", default="1.0")
+ap.add_argument("--reps", type=int, default=5)
+a = ap.parse_args()
+ctx = tc.default_context()
+lib = _lib.load()
+setflags = lib.tc_debug_set_search_flags
+setflags.argtypes = [C.c_int]
+flags = [int(f) for f in a.flags.split(",")]
+scales = [float(s) for s in a.cellscale.split(",")]
+
+
+def timed(fn, reps):
+    fn()
+    ctx.synchronize()
+    ts = []
+    for _ in range(reps):
+        ctx.timer_start()
+        fn()
+        ts.append(ctx.timer_stop())
+    return float(np.median(ts))
+
+
+def normals_case(name, pts, k):
+    cloud = tc.DeviceCloud(pts, ctx)
+    n = len(pts)
+    d_out = ctx.alloc(n * 24)
+    base_index = tc.GridIndex(cloud, k_hint=k)
+    auto = base_index.info()["cell_size"]
+    ref = None
+    for sc in scales:
+        index = base_index if sc == 1.0 else tc.GridIndex(cloud, k_hint=k, cell_size=auto * sc)
+        info = index.info()
+        for f in flags:
+            setflags(f)
+            ms = timed(lambda: index.estimate_normals_device(d_out, k), a.reps)
+            out = np.empty((n, 6), np.float32)
+            ctx.to_host(out, d_out)
+            if ref is None:
+                ref = out
+            same = np.array_equal(ref, out)
+            print(f"{name:4s} k={k:2d} cell={info['cell_size']:.4f} (x{sc}) occ={info['occupied_cells']} "
+                  f"maxpop={info['max_cell_population']} flags={f} kernel={ms:8.3f} ms "
+                  f"{n / ms / 1e3:8.1f} Mpts/s same={same}", flush=True)
+        if index is not base_index:
+            index.free()
+    ctx.free(d_out)
+
+
+what = a.what.split(",")
+if "c2" in what:
+    normals_case("c2", synth.kitti_frame(), 16)
+if "c4" in what:
+    n = a.c4n
+    normals_case("c4", synth.terrain(n, 100.0 * (n / 1e7) ** 0.5, seed=4, noise=0.002), 30)
+if "c3" in what:
+    n = 1_000_000
+    src, tgt, nrm, T = synth.scan_pair(n, half_extent=50.0)
+    tcloud, scloud = tc.DeviceCloud(tgt, ctx), tc.DeviceCloud(src, ctx)
+    d_nrm = ctx.alloc(n * 12)
+    ctx.to_device(d_nrm, nrm)
+    base_index = tc.GridIndex(tcloud, k_hint=1)
+    auto = base_index.info()["cell_size"]
+    ref = None
+    for sc in scales:
+        index = base_index if sc == 1.0 else tc.GridIndex(tcloud, k_hint=1, cell_size=auto * sc)
+        info = index.info()
+        for f in flags:
+            setflags(f)
+            res = []
+            ms = timed(lambda: res.append(tc.icp_point_to_plane_device(
+                scloud, index, d_nrm, tc.IDENTITY, 30, None, -1.0)), 3)
+            r = res[-1]
+            if ref is None:
+                ref = r.transformation
+            print(f"c3 icp cell={info['cell_size']:.4f} (x{sc}) occ={info['occupied_cells']} "
+                  f"maxpop={info['max_cell_population']} flags={f} total={ms:8.3f} ms "
+                  f"per_iter={ms / 30 * 1e3:7.1f} us same={np.array_equal(ref, r.transformation)}",
+                  flush=True)

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: runs one workload a few times (no timing, no oracle).
+
+    python tools/profile_targets.py c2|c4|c3|knn [--n N] [--reps R]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import threecrate_b200 as tc  # noqa: E402
+from threecrate_b200 import synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what", choices=["c2", "c4", "c3", "knn"])
+ap.add_argument("--n", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+ctx = tc.default_context()
+
+if a.what in ("c2", "knn"):
+    pts = synth.kitti_frame()
+    cloud = tc.DeviceCloud(pts, ctx)
+    d_out = ctx.alloc(len(pts) * 24)
+    for _ in range(a.reps):
+        index = tc.GridIndex(cloud, k_hint=16)
+        if a.what == "c2":
+            index.estimate_normals_device(d_out, 16)
+        else:
+            index.knn(None, 16, exclude_self=True)
+        ctx.synchronize()
+        print(index.info())
+        index.free()
+elif a.what == "c4":
+    n = a.n or 10_000_000
+    pts = synth.terrain(n, 100.0 * (n / 1e7) ** 0.5, seed=4, noise=0.002)
+    cloud = tc.DeviceCloud(pts, ctx)
+    d_out = ctx.alloc(n * 24)
+    for _ in range(a.reps):
+        index = tc.GridIndex(cloud, k_hint=30)
+        index.estimate_normals_device(d_out, 30)
+        ctx.synchronize()
+        print(index.info())
+        index.free()
+elif a.what == "c3":
+    n = a.n or 1_000_000
+    src, tgt, nrm, T = synth.scan_pair(n, half_extent=50.0 * (n / 1e6) ** 0.5)
+    tcloud, scloud = tc.DeviceCloud(tgt, ctx), tc.DeviceCloud(src, ctx)
+    d_nrm = ctx.alloc(n * 12)
+    ctx.to_device(d_nrm, nrm)
+    for _ in range(a.reps):
+        index = tc.GridIndex(tcloud, k_hint=1)
+        r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, 5, None, -1.0)
+        print(index.info(), r.translation)
+        index.free()
