@@ -18,37 +18,182 @@ namespace {
 constexpr int kBlock = 128;
 using namespace tcs;
 
+// Two-pass exact selection for one query (see k_knn2).  On success the sorted positions (into
+// `pts`) of the neighbours, ascending by (d2, index), are in s_b[0 .. n)[threadIdx.x] and n is
+// returned; -1 means "ties: use the exact chain kernel" (bit-equal d2 inside the list, or more
+// than `need` points at or below the K-th d2).
+//   pass 1  SelF: exact K-th squared distance tau (floats only, sorting networks)
+//   pass 2  re-scan the rows that can hold d2 <= tau, append each member's position to s_a
+//           (a 4-instruction append, so lanes that accept different candidates cost little)
+//   rank    uniform loop over the n members: slot = #{v[i] < d2}; s_b[slot] = position
+template <int L>
+__device__ __forceinline__ int select_two_pass(const GridParams& g, const float4* __restrict__ pts,
+                                               const uint32_t* __restrict__ cell_start, float qx,
+                                               float qy, float qz, uint32_t need,
+                                               uint32_t (*s_a)[kBlock], uint32_t (*s_b)[kBlock]) {
+  SelF<L> sel;
+  sel.pad = L - (int)need;
+  const int R = grid_search(g, pts, cell_start, qx, qy, qz, sel);
+  const float tau = sel.kth();  // +inf when fewer than `need` points exist: everything is kept
+  // bit-equal real entries would collide in the rank placement -> exact chain kernel instead
+  bool tie = false;
+#pragma unroll
+  for (int i = 0; i + 1 < L; ++i)
+    if (sel.v[i] == sel.v[i + 1] && sel.v[i] >= 0.0f && sel.v[i] < INFINITY) tie = true;
+  if (tie) return -1;
+  uint32_t n = 0;
+  grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t j = lo; j < hi; ++j) {
+      const float4 c = __ldg(&pts[j]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+      if (d2 <= tau) {
+        if (n < (uint32_t)L) s_a[n][threadIdx.x] = j;
+        ++n;
+      }
+    }
+  });
+  if (n > need) return -1;  // tie straddling rank `need`: membership is decided by the index
+#pragma unroll 1
+  for (uint32_t m = 0; m < n; ++m) {
+    const uint32_t j = s_a[m][threadIdx.x];
+    const float4 c = __ldg(&pts[j]);
+    const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+    int rank = -sel.pad;  // the sentinels are always below d2
+#pragma unroll
+    for (int i = 0; i < L; ++i) rank += (sel.v[i] < d2) ? 1 : 0;
+    s_b[rank][threadIdx.x] = j;
+  }
+  return (int)n;
+}
+
 // ---------------------------------------------------------------------------------- kNN kernel
+// kNN(k+1), retain idx != i, truncate k  (point_cloud_ops.rs:91-99); plain kNN otherwise.
+// `key` is the ascending (d2, index) list; entries == kEmpty are padding.
+// Neighbour source for the emit functions.
+//  RegKeys  : the u64 (d2, index) register list of the chain kernels (static indices, unrolled);
+//             coordinates come from the original-order xyz array.
+//  SortedPos: positions into the cell-sorted float4 array (shared-memory column, rolled loop);
+//             one 128-bit load yields coordinates and index, d2 is recomputed.
+struct Nb {
+  float x, y, z, d2;
+  uint32_t id;
+  bool valid;
+};
 template <int K>
-__global__ void __launch_bounds__(kBlock)
-k_knn(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-      const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end, uint32_t k,
-      int drop_self, uint32_t* __restrict__ idx_out, float* __restrict__ dist_out,
-      uint32_t* __restrict__ count_out) {
-  const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
-  if (qi >= q_end) return;
-  const float4 q = __ldg(&queries[qi]);
-  const uint32_t qid = __float_as_uint(q.w);  // original query index = output row
-  TopK<K> tk;
-  grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
-  // kNN(k+1), retain idx != i, truncate k  (point_cloud_ops.rs:91-99); plain kNN otherwise
+struct RegKeys {
+  const uint64_t (&key)[K];
+  const float* __restrict__ xyz;
+  static constexpr int kCount = K;
+  static constexpr bool kUnroll = true;
+  __device__ __forceinline__ int count() const { return K; }
+  __device__ __forceinline__ Nb head(int i) const {  // index + d2 only
+    Nb r;
+    r.valid = key[i] != kEmpty;
+    r.id = (uint32_t)key[i];
+    r.d2 = __uint_as_float((uint32_t)(key[i] >> 32));
+    r.x = r.y = r.z = 0.0f;
+    return r;
+  }
+  __device__ __forceinline__ void coords(Nb& r) const {
+    const float* p = xyz + 3 * (uint64_t)r.id;
+    r.x = __ldg(p + 0);
+    r.y = __ldg(p + 1);
+    r.z = __ldg(p + 2);
+  }
+};
+struct SortedPos {
+  uint32_t (*col)[kBlock];
+  int n;
+  const float4* __restrict__ pts;
+  float qx, qy, qz;
+  static constexpr int kCount = 1;
+  static constexpr bool kUnroll = false;
+  __device__ __forceinline__ int count() const { return n; }
+  __device__ __forceinline__ Nb head(int i) const {
+    const float4 c = __ldg(&pts[col[i][threadIdx.x]]);
+    Nb r;
+    r.valid = true;
+    r.x = c.x;
+    r.y = c.y;
+    r.z = c.z;
+    r.id = __float_as_uint(c.w);
+    r.d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+    return r;
+  }
+  __device__ __forceinline__ void coords(Nb&) const {}
+};
+
+template <class KS>
+__device__ __forceinline__ void knn_emit(const KS& keys, uint32_t qid, uint32_t k, int drop_self,
+                                         uint32_t* __restrict__ idx_out,
+                                         float* __restrict__ dist_out,
+                                         uint32_t* __restrict__ count_out) {
   uint32_t c = 0;
   const uint64_t row = (uint64_t)qid * k;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    const uint64_t key = tk.key[i];
-    const uint32_t id = (uint32_t)key;
-    if (key != kEmpty && c < k && !(drop_self && id == qid)) {
-      idx_out[row + c] = id;
-      if (dist_out) dist_out[row + c] = xsqrt(__uint_as_float((uint32_t)(key >> 32)));
+  auto body = [&](int i) {
+    const Nb nb = keys.head(i);
+    if (nb.valid && c < k && !(drop_self && nb.id == qid)) {
+      idx_out[row + c] = nb.id;
+      if (dist_out) dist_out[row + c] = xsqrt(nb.d2);
       ++c;
     }
+  };
+  if (KS::kUnroll) {
+#pragma unroll
+    for (int i = 0; i < KS::kCount; ++i) body(i);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < keys.count(); ++i) body(i);
   }
   if (count_out) count_out[qid] = c;
   for (uint32_t j = c; j < k; ++j) {
     idx_out[row + j] = TC_NO_INDEX;
     if (dist_out) dist_out[row + j] = INFINITY;
   }
+}
+
+// Exact u64 insertion-chain kernel.  With `list` == nullptr it processes queries
+// [q_begin, q_end); otherwise the query positions listed in list[0 .. *list_count) (the
+// tie-overflow fallback of the two-pass kernels), grid-stride.
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+k_knn(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+      const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end, uint32_t k,
+      int drop_self, uint32_t* __restrict__ idx_out, float* __restrict__ dist_out,
+      uint32_t* __restrict__ count_out, const uint32_t* __restrict__ list,
+      const uint32_t* __restrict__ list_count) {
+  const uint32_t total = list ? *list_count : (q_end - q_begin);
+  for (uint32_t t = blockIdx.x * kBlock + threadIdx.x; t < total; t += gridDim.x * kBlock) {
+    const uint32_t qi = list ? list[t] : q_begin + t;
+    const float4 q = __ldg(&queries[qi]);
+    const uint32_t qid = __float_as_uint(q.w);  // original query index = output row
+    TopK<K> tk;
+    grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
+    knn_emit(RegKeys<K>{tk.key, nullptr}, qid, k, drop_self, idx_out, dist_out, count_out);
+  }
+}
+
+// Two-pass kernel: pass 1 finds the exact K-th squared distance with the float selection list,
+// pass 2 re-scans and collects the (d2, index) keys with d2 <= tau into shared memory, which a
+// single u64 bitonic sort then orders.  More than L members (ties) -> fallback list.
+template <int L>
+__global__ void __launch_bounds__(kBlock)
+k_knn2(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+       const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end, uint32_t k,
+       uint32_t need, int drop_self, uint32_t* __restrict__ idx_out, float* __restrict__ dist_out,
+       uint32_t* __restrict__ count_out, uint32_t* __restrict__ fb_list,
+       uint32_t* __restrict__ fb_count) {
+  __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
+  const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
+  if (qi >= q_end) return;
+  const float4 q = __ldg(&queries[qi]);
+  const uint32_t qid = __float_as_uint(q.w);
+  const int n = select_two_pass<L>(g, pts, cell_start, q.x, q.y, q.z, need, s_a, s_b);
+  if (n < 0) {
+    fb_list[atomicAdd(fb_count, 1u)] = qi;
+    return;
+  }
+  knn_emit(SortedPos{s_b, n, pts, q.x, q.y, q.z}, qid, k, drop_self, idx_out, dist_out, count_out);
 }
 
 // ------------------------------------------------------------------------- symmetric 3x3 eigen
@@ -104,33 +249,31 @@ __device__ __forceinline__ void smallest_eigvec(const float cov[6] /*xx,xy,xz,yy
 }
 
 // ------------------------------------------------------------------------------ normals kernel
-template <int K>
-__global__ void __launch_bounds__(kBlock)
-k_normals(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-          const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end, uint32_t k, int orient,
-          float vpx, float vpy, float vpz, float* __restrict__ out) {
-  const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
-  if (qi >= q_end) return;
-  const float4 q = __ldg(&pts[qi]);
-  const uint32_t qid = __float_as_uint(q.w);
-  TopK<K> tk;
-  grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
-
+// Normal of one point from its ascending (d2, index) neighbour keys (normals.rs:306-354 body).
+template <class KS>
+__device__ __forceinline__ void normals_emit(const KS& keys, const float4 q, uint32_t qid,
+                                             uint32_t k, int orient, float vpx, float vpy,
+                                             float vpz, float* __restrict__ out) {
   // neighbourhood = first k of kNN(k+1) with self dropped by index, then self appended last
   // (normals.rs:148-153, 338-340).  Sums are sequential f32 in that order (normals.rs:165-177).
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
   uint32_t cnt = 0;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    const uint64_t key = tk.key[i];
-    const uint32_t id = (uint32_t)key;
-    if (key != kEmpty && cnt < k && id != qid) {
-      const float* p = xyz + 3 * (uint64_t)id;
-      sx = xadd(sx, __ldg(p + 0));
-      sy = xadd(sy, __ldg(p + 1));
-      sz = xadd(sz, __ldg(p + 2));
+  auto sum_body = [&](int i) {
+    Nb nb = keys.head(i);
+    if (nb.valid && cnt < k && nb.id != qid) {
+      keys.coords(nb);
+      sx = xadd(sx, nb.x);
+      sy = xadd(sy, nb.y);
+      sz = xadd(sz, nb.z);
       ++cnt;
     }
+  };
+  if (KS::kUnroll) {
+#pragma unroll
+    for (int i = 0; i < KS::kCount; ++i) sum_body(i);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < keys.count(); ++i) sum_body(i);
   }
   sx = xadd(sx, q.x);
   sy = xadd(sy, q.y);
@@ -141,33 +284,32 @@ k_normals(GridParams g, const float4* __restrict__ pts, const uint32_t* __restri
     const float fn = (float)nn;
     const float cx = xdiv(sx, fn), cy = xdiv(sy, fn), cz = xdiv(sz, fn);
     float c[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t cnt2 = 0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const uint64_t key = tk.key[i];
-      const uint32_t id = (uint32_t)key;
-      if (key != kEmpty && cnt2 < k && id != qid) {
-        const float* p = xyz + 3 * (uint64_t)id;
-        const float dx = xsub(__ldg(p + 0), cx), dy = xsub(__ldg(p + 1), cy),
-                    dz = xsub(__ldg(p + 2), cz);
-        c[0] = xadd(c[0], xmul(dx, dx));
-        c[1] = xadd(c[1], xmul(dx, dy));
-        c[2] = xadd(c[2], xmul(dx, dz));
-        c[3] = xadd(c[3], xmul(dy, dy));
-        c[4] = xadd(c[4], xmul(dy, dz));
-        c[5] = xadd(c[5], xmul(dz, dz));
-        ++cnt2;
-      }
-    }
-    {
-      const float dx = xsub(q.x, cx), dy = xsub(q.y, cy), dz = xsub(q.z, cz);
+    auto acc = [&](float px, float py, float pz) {
+      const float dx = xsub(px, cx), dy = xsub(py, cy), dz = xsub(pz, cz);
       c[0] = xadd(c[0], xmul(dx, dx));
       c[1] = xadd(c[1], xmul(dx, dy));
       c[2] = xadd(c[2], xmul(dx, dz));
       c[3] = xadd(c[3], xmul(dy, dy));
       c[4] = xadd(c[4], xmul(dy, dz));
       c[5] = xadd(c[5], xmul(dz, dz));
+    };
+    uint32_t cnt2 = 0;
+    auto cov_body = [&](int i) {
+      Nb nb = keys.head(i);
+      if (nb.valid && cnt2 < k && nb.id != qid) {
+        keys.coords(nb);
+        acc(nb.x, nb.y, nb.z);
+        ++cnt2;
+      }
+    };
+    if (KS::kUnroll) {
+#pragma unroll
+      for (int i = 0; i < KS::kCount; ++i) cov_body(i);
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < keys.count(); ++i) cov_body(i);
     }
+    acc(q.x, q.y, q.z);
 #pragma unroll
     for (int i = 0; i < 6; ++i) c[i] = xdiv(c[i], fn);
     smallest_eigvec(c, nrm);
@@ -206,6 +348,54 @@ k_normals(GridParams g, const float4* __restrict__ pts, const uint32_t* __restri
   o[5] = nrm[2];
 }
 
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+k_normals(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+          const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end, uint32_t k, int orient,
+          float vpx, float vpy, float vpz, float* __restrict__ out,
+          const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
+          uint32_t* __restrict__ dbg) {
+  const uint32_t total = list ? *list_count : (q_end - q_begin);
+  for (uint32_t t = blockIdx.x * kBlock + threadIdx.x; t < total; t += gridDim.x * kBlock) {
+    const uint32_t qi = list ? list[t] : q_begin + t;
+    const float4 q = __ldg(&pts[qi]);
+    const uint32_t qid = __float_as_uint(q.w);
+    const long long t0 = dbg ? clock64() : 0;
+    TopK<K> tk;
+    const int R = grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
+    normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
+    if (dbg) {  // per-query cycles and final block radius (tools/kbench.py --dbg)
+      dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
+      dbg[2 * (size_t)qid + 1] = (uint32_t)R;
+    }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock)
+k_normals2(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+           const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end, uint32_t k, int orient,
+           float vpx, float vpy, float vpz, float* __restrict__ out,
+           uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
+           uint32_t* __restrict__ dbg) {
+  __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
+  const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
+  if (qi >= q_end) return;
+  const float4 q = __ldg(&pts[qi]);
+  const uint32_t qid = __float_as_uint(q.w);
+  const long long t0 = dbg ? clock64() : 0;
+  const int n = select_two_pass<L>(g, pts, cell_start, q.x, q.y, q.z, k + 1, s_a, s_b);
+  if (n < 0) {
+    fb_list[atomicAdd(fb_count, 1u)] = qi;
+    return;
+  }
+  normals_emit(SortedPos{s_b, n, pts, q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz, out);
+  if (dbg) {
+    dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
+    dbg[2 * (size_t)qid + 1] = (uint32_t)n;
+  }
+}
+
 // smallest instantiated list size >= need (0 if unsupported)
 constexpr int kSizes[] = {1, 2, 4, 6, 8, 11, 13, 17, 21, 25, 31, 33, 40, 48, 64};
 inline int pick_size(uint32_t need) {
@@ -216,8 +406,10 @@ inline int pick_size(uint32_t need) {
 
 }  // namespace
 
-int g_tc_search_flags = 3;
+int g_tc_search_flags = 7;
+static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (2 u32 / point)
 extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
+extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint32_t*)d_buf; }
 
 #define TC_DISPATCH_K(SZ, CALL)                     \
   switch (SZ) {                                     \
@@ -239,6 +431,7 @@ extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags
     default: break;                                 \
   }
 
+// flags bit 2 (value 4): two-pass float selection (k_knn2 / k_normals2) when need <= 32.
 int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_sorted,
                    uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out) {
@@ -252,10 +445,36 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   const dim3 grid((nq + kBlock - 1) / kBlock);
   GridParams gp = ix->g;
   gp.flags = g_tc_search_flags;
-  TC_DISPATCH_K(sz, (k_knn<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                        gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, (uint32_t)q_begin,
-                        (uint32_t)q_end, k, drop_self, d_idx_out, d_dist_out, d_count_out)));
+  const bool two_pass = (gp.flags & 4) && need <= 32 && need >= 2;
+  if (!two_pass) {
+    TC_DISPATCH_K(sz, (k_knn<KK><<<grid, kBlock, 0, ctx->stream>>>(
+                          gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, (uint32_t)q_begin,
+                          (uint32_t)q_end, k, drop_self, d_idx_out, d_dist_out, d_count_out,
+                          nullptr, nullptr)));
+    TC_LAUNCHED(ctx);
+    return TC_OK;
+  }
+  uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions that overflowed on ties
+  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
+  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  gp.flags |= 2;  // row pruning is always worth it here
+  if (need <= 16)
+    k_knn2<16><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start, d_queries_sorted,
+                                                 (uint32_t)q_begin, (uint32_t)q_end, k, need,
+                                                 drop_self, d_idx_out, d_dist_out, d_count_out,
+                                                 d_fb + 1, d_fb);
+  else
+    k_knn2<32><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start, d_queries_sorted,
+                                                 (uint32_t)q_begin, (uint32_t)q_end, k, need,
+                                                 drop_self, d_idx_out, d_dist_out, d_count_out,
+                                                 d_fb + 1, d_fb);
   TC_LAUNCHED(ctx);
+  const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
+  TC_DISPATCH_K(sz, (k_knn<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
+                        gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, 0u, 0u, k, drop_self,
+                        d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)));
+  TC_LAUNCHED(ctx);
+  tc_free(ctx, d_fb);
   return TC_OK;
 }
 
@@ -269,9 +488,35 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const dim3 grid((nq + kBlock - 1) / kBlock);
   GridParams gp = ix->g;
   gp.flags = g_tc_search_flags;
-  TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                        gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, (uint32_t)q_begin,
-                        (uint32_t)q_end, k, orient, vp[0], vp[1], vp[2], d_out_aos)));
+  const bool two_pass = (gp.flags & 4) && k + 1 <= 32;
+  if (!two_pass) {
+    TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
+                          gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, (uint32_t)q_begin,
+                          (uint32_t)q_end, k, orient, vp[0], vp[1], vp[2], d_out_aos, nullptr,
+                          nullptr, g_tc_dbg)));
+    TC_LAUNCHED(ctx);
+    return TC_OK;
+  }
+  uint32_t* d_fb = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
+  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  gp.flags |= 2;
+  if (k + 1 <= 16)
+    k_normals2<16><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start,
+                                                     ix->cloud->d_xyz, (uint32_t)q_begin,
+                                                     (uint32_t)q_end, k, orient, vp[0], vp[1],
+                                                     vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
+  else
+    k_normals2<32><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start,
+                                                     ix->cloud->d_xyz, (uint32_t)q_begin,
+                                                     (uint32_t)q_end, k, orient, vp[0], vp[1],
+                                                     vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
   TC_LAUNCHED(ctx);
+  const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
+  TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
+                        gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, 0u, 0u, k, orient, vp[0],
+                        vp[1], vp[2], d_out_aos, d_fb + 1, d_fb, nullptr)));
+  TC_LAUNCHED(ctx);
+  tc_free(ctx, d_fb);
   return TC_OK;
 }

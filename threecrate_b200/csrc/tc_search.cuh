@@ -64,6 +64,116 @@ struct TopK {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Register sorting networks (all indices compile-time, so arrays stay in registers).
+// A float compare-exchange is two ALU ops (FMNMX min/max) and branch-free.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void bitonic_sort_f(float (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+          if ((i & k) == 0) {
+            a[i] = lo;
+            a[l] = hi;
+          } else {
+            a[i] = hi;
+            a[l] = lo;
+          }
+        }
+      }
+    }
+  }
+}
+// a is bitonic on entry, ascending on exit
+template <int N>
+__device__ __forceinline__ void bitonic_merge_f(float (&a)[N]) {
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int l = i ^ j;
+      if (l > i) {
+        const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+        a[i] = lo;
+        a[l] = hi;
+      }
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool sw = ((i & k) == 0) ? (a[l] < a[i]) : (a[i] < a[l]);
+          const uint64_t x = a[i], y = a[l];
+          a[i] = sw ? y : x;
+          a[l] = sw ? x : y;
+        }
+      }
+    }
+  }
+}
+
+// Pass-1 accumulator of the two-pass selection: the smallest squared distances seen so far,
+// ascending, indices NOT carried.  The list always has L entries; to select the `need`-th
+// smallest with need <= L, the front is pre-filled with (L - need) sentinels of -1 (below any
+// d2), which never move: the real values live in v[L-need .. L-1] and the K-th smallest is the
+// STATIC register v[L-1] (a runtime index into v[] would be lowered to select chains).
+// Candidates are taken L at a time; a batch holding something below the current K-th distance
+// is sorted and merged:  m[i] = min(v[i], b[L-1-i]) keeps the L smallest of the 2L and is
+// bitonic -> log2(L) merge stages.  A float compare-exchange is 2 FMNMX, branch-free.
+template <int L>
+struct SelF {
+  float v[L];
+  int pad;  // L - need
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < L; ++i) v[i] = (i < pad) ? -1.0f : INFINITY;
+  }
+  __device__ __forceinline__ bool full() const { return v[L - 1] < INFINITY; }
+  __device__ __forceinline__ float kth() const { return v[L - 1]; }
+  __device__ __forceinline__ void merge(float (&b)[L]) {
+    bitonic_sort_f<L>(b);
+#pragma unroll
+    for (int i = 0; i < L; ++i) v[i] = fminf(v[i], b[L - 1 - i]);
+    bitonic_merge_f<L>(v);
+  }
+  __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
+                                       float qx, float qy, float qz, int) {
+    if (lo >= hi) return;
+    const uint32_t last = hi - 1;
+#pragma unroll 1
+    for (uint32_t base = lo; base < hi; base += L) {
+      float b[L];
+      float bm = INFINITY;
+#pragma unroll
+      for (int t = 0; t < L; ++t) {
+        // unconditional load from a clamped index: the loads of a batch are independent and
+        // can all be in flight together; out-of-range slots are masked to +inf afterwards
+        const uint32_t j = min(base + t, last);
+        const float4 c = __ldg(&pts[j]);
+        const float d = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+        b[t] = (base + t <= last) ? d : INFINITY;
+        bm = fminf(bm, b[t]);
+      }
+      if (bm < v[L - 1]) merge(b);  // strict: a candidate equal to the K-th distance cannot lower it
+    }
+  }
+};
+
 // Conservative lower bound on the distance from the query to any indexed point whose cell lies
 // outside the block [c-R, c+R]^3.  In cell units a point beyond the +side of an axis differs by
 // more than (R + 1 - f), beyond the -side by more than (f + R) (f = u - c, the query's fractional
@@ -120,9 +230,9 @@ __device__ __forceinline__ float row_gap(int d, float f) {
 // Exact nearest-neighbour search for one query; Acc is TopK<K> or Best1.
 // flags: bit 0 deferred insertion (TopK), bit 1 prune rows that cannot beat the K-th distance.
 template <class Acc>
-__device__ __forceinline__ void grid_search(const GridParams& g, const float4* __restrict__ pts,
-                                            const uint32_t* __restrict__ cell_start, float qx,
-                                            float qy, float qz, Acc& tk) {
+__device__ __forceinline__ int grid_search(const GridParams& g, const float4* __restrict__ pts,
+                                           const uint32_t* __restrict__ cell_start, float qx,
+                                           float qy, float qz, Acc& tk) {
   tk.init();
   const int flags = g.flags;
   float ux, uy, uz;
@@ -133,55 +243,109 @@ __device__ __forceinline__ void grid_search(const GridParams& g, const float4* _
   const float mx = g.ex + fabsf(qx - g.ox), my = g.ey + fabsf(qy - g.oy),
               mz = g.ez + fabsf(qz - g.oz);
 
-  auto scan_row = [&](int y, int z, int xa, int xb) {
-    if ((flags & 2) && tk.full()) {
-      const float by = axis_bound(row_gap(y - cy, fy), g.cell, my);
-      const float bz = axis_bound(row_gap(z - cz, fz), g.cell, mz);
-      if ((by * by + bz * bz) * 0.99999f > tk.kth()) return;  // every point here is farther
-    }
-    const uint32_t row = cell_id(g, 0, y, z);
-    const uint32_t lo = __ldg(&cell_start[row + xa]);
-    const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
-    tk.scan(pts, lo, hi, qx, qy, qz, flags);
-  };
-
-  // rings 0 and 1: the 3x3 rows around the query's row, x-range [cx-1, cx+1] (contiguous);
-  // the query's own row goes first so the K-th distance tightens before the others are tested
-  {
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    scan_row(cy, cz, x0, x1);
-    for (int dz = -1; dz <= 1; ++dz) {
+  // One loop nest visits the block of radius R = 1 (rings 0 and 1 together), then thicker and
+  // thicker shells (Rp, R] until the K-th best d2 is provably final.  While the list is not even
+  // full the radius doubles (isolated points would otherwise pay O(R^3) dependent table look-ups);
+  // once full it grows by one.  Rows are taken from the query's own row outwards (offsets
+  // 0,-1,+1,-2,+2,...) so the K-th distance tightens early, and there is a SINGLE tk.scan call
+  // site: the unrolled selection networks are instantiated once (I-cache).
+  int R = 1, Rp = -1;  // current block radius, radius already searched
+  while (true) {
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+    for (int iz = 0; iz <= 2 * R; ++iz) {
+      const int dz = ((iz + 1) >> 1) * ((iz & 1) ? -1 : 1);
       const int z = cz + dz;
       if (z < 0 || z >= g.nz) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
+      for (int iy = 0; iy <= 2 * R; ++iy) {
+        const int dy = ((iy + 1) >> 1) * ((iy & 1) ? -1 : 1);
         const int y = cy + dy;
-        if (y < 0 || y >= g.ny || (dy == 0 && dz == 0)) continue;
-        scan_row(y, z, x0, x1);
-      }
-    }
-  }
-  int R = 1;
-  while (true) {
-    const float b = ring_bound(g, R, cx, cy, cz, fx, fy, fz, mx, my, mz);
-    if (b == INFINITY) break;  // the searched block already covers the whole grid
-    if (tk.full()) {
-      if (tk.kth() < b * b * 0.99999f) break;
-    }
-    ++R;
-    // shell R: full x-range on rows with max(|dy|,|dz|) == R, the two end cells elsewhere
-    const int zlo = max(cz - R, 0), zhi = min(cz + R, g.nz - 1);
-    const int ylo = max(cy - R, 0), yhi = min(cy + R, g.ny - 1);
-    const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-    for (int z = zlo; z <= zhi; ++z) {
-      for (int y = ylo; y <= yhi; ++y) {
-        const bool outer = (abs(z - cz) == R) || (abs(y - cy) == R);
-        if (outer) {
-          scan_row(y, z, x0, x1);
-        } else {
-          if (cx - R >= 0) scan_row(y, z, cx - R, cx - R);
-          if (cx + R <= g.nx - 1) scan_row(y, z, cx + R, cx + R);
+        if (y < 0 || y >= g.ny) continue;
+        // rows outside the previous block get their full x-range, rows inside it only the two
+        // new end ranges [cx-R, cx-Rp-1] and [cx+Rp+1, cx+R]
+        const bool outer = (abs(dz) > Rp) || (abs(dy) > Rp);
+        float byz = 0.0f;
+        const bool prune = (flags & 2) && tk.full();
+        if (prune) {
+          const float by = axis_bound(row_gap(dy, fy), g.cell, my);
+          const float bz = axis_bound(row_gap(dz, fz), g.cell, mz);
+          byz = by * by + bz * bz;
+          if (byz * 0.99999f > tk.kth()) continue;  // every point of the row is farther
+        }
+        const uint32_t row = cell_id(g, 0, y, z);
+        for (int seg = 0; seg < (outer ? 1 : 2); ++seg) {
+          int xa, xb;
+          if (outer) {
+            xa = x0;
+            xb = x1;
+          } else if (seg == 0) {
+            xa = x0;
+            xb = cx - Rp - 1;
+          } else {
+            xa = cx + Rp + 1;
+            xb = x1;
+          }
+          if (prune) {  // trim cells that cannot beat the K-th distance from both ends
+            const float kth = tk.kth();
+            while (xa < cx && xa <= xb) {
+              const float bx = axis_bound(row_gap(xa - cx, fx), g.cell, mx);
+              if ((byz + bx * bx) * 0.99999f > kth) ++xa; else break;
+            }
+            while (xb > cx && xb >= xa) {
+              const float bx = axis_bound(row_gap(xb - cx, fx), g.cell, mx);
+              if ((byz + bx * bx) * 0.99999f > kth) --xb; else break;
+            }
+          }
+          if (xa > xb) continue;
+          const uint32_t lo = __ldg(&cell_start[row + xa]);
+          const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
+          tk.scan(pts, lo, hi, qx, qy, qz, flags);
         }
       }
+    }
+    const float b = ring_bound(g, R, cx, cy, cz, fx, fy, fz, mx, my, mz);
+    if (b == INFINITY) break;  // the searched block already covers the whole grid
+    if (tk.full() && tk.kth() < b * b * 0.99999f) break;
+    Rp = R;
+    R = tk.full() ? R + 1 : 2 * R;
+  }
+  return R;
+}
+
+// Second traversal for the two-pass selection: visit every row of the block [c-R, c+R]^3 whose
+// conservative distance bound does not exceed tau (the final K-th squared distance) and hand its
+// candidate range to `f`.  Exact: a skipped row cannot hold a point with d2 <= tau.
+template <class F>
+__device__ __forceinline__ void grid_visit(const GridParams& g, const uint32_t* __restrict__ cell_start,
+                                           float qx, float qy, float qz, int R, float tau, F&& f) {
+  float ux, uy, uz;
+  const int cx = cell_coord(qx, g.ox, g.inv, g.nx, ux);
+  const int cy = cell_coord(qy, g.oy, g.inv, g.ny, uy);
+  const int cz = cell_coord(qz, g.oz, g.inv, g.nz, uz);
+  const float fx = ux - (float)cx, fy = uy - (float)cy, fz = uz - (float)cz;
+  const float mx = g.ex + fabsf(qx - g.ox), my = g.ey + fabsf(qy - g.oy),
+              mz = g.ez + fabsf(qz - g.oz);
+  const int zlo = max(cz - R, 0), zhi = min(cz + R, g.nz - 1);
+  const int ylo = max(cy - R, 0), yhi = min(cy + R, g.ny - 1);
+  const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+  for (int z = zlo; z <= zhi; ++z) {
+    const float bz = axis_bound(row_gap(z - cz, fz), g.cell, mz);
+    for (int y = ylo; y <= yhi; ++y) {
+      const float by = axis_bound(row_gap(y - cy, fy), g.cell, my);
+      const float byz = by * by + bz * bz;
+      if (byz * 0.99999f > tau) continue;
+      int xa = x0, xb = x1;  // trim cells that cannot hold a point with d2 <= tau
+      while (xa < cx) {
+        const float bx = axis_bound(row_gap(xa - cx, fx), g.cell, mx);
+        if ((byz + bx * bx) * 0.99999f > tau) ++xa; else break;
+      }
+      while (xb > cx) {
+        const float bx = axis_bound(row_gap(xb - cx, fx), g.cell, mx);
+        if ((byz + bx * bx) * 0.99999f > tau) --xb; else break;
+      }
+      const uint32_t row = cell_id(g, 0, y, z);
+      const uint32_t lo = __ldg(&cell_start[row + xa]);
+      const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
+      f(lo, hi);
     }
   }
 }
