@@ -88,6 +88,8 @@ typedef struct tc_index_info {
   float bbox_max[3];
   uint32_t occupied_cells;
   uint32_t max_cell_population;
+  uint32_t n_levels; /* grid resolutions built (1 unless the density is strongly skewed) */
+  uint32_t reserved;
 } tc_index_info;
 int tc_index_get_info(const tc_index* index, tc_index_info* out);
 

@@ -37,7 +37,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.IcpResultC) == 48  # 7 f32 + f32 + u32 + i32 + (pad) + u64
     assert _lib.IcpResultC.n_correspondences.offset == 40
-    assert C.sizeof(_lib.IndexInfoC) == 64
+    assert C.sizeof(_lib.IndexInfoC) == 72
 
 
 def test_sass_is_sm100a_only():

@@ -40,7 +40,8 @@ class IcpResultC(C.Structure):
 class IndexInfoC(C.Structure):
     _fields_ = [("n_points", C.c_uint64), ("n_cells", C.c_uint64), ("dims", C.c_uint32 * 3),
                 ("cell_size", C.c_float), ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
-                ("occupied_cells", C.c_uint32), ("max_cell_population", C.c_uint32)]
+                ("occupied_cells", C.c_uint32), ("max_cell_population", C.c_uint32),
+                ("n_levels", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _vp = C.c_void_p

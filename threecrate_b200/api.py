@@ -176,7 +176,7 @@ class GridIndex:
         return {"n_points": inf.n_points, "n_cells": inf.n_cells, "dims": tuple(inf.dims),
                 "cell_size": inf.cell_size, "bbox_min": tuple(inf.bbox_min),
                 "bbox_max": tuple(inf.bbox_max), "occupied_cells": inf.occupied_cells,
-                "max_cell_population": inf.max_cell_population}
+                "max_cell_population": inf.max_cell_population, "n_levels": inf.n_levels}
 
     def free(self):
         if getattr(self, "h", None):

@@ -247,13 +247,13 @@ extern "C" int tc_knn_device(tc_context* ctx, const tc_index* ix, const float* d
   }
   if (!d_idx_out) return TC_INVALID_DATA;
   if (self_query)
-    return tci_knn_launch(ctx, ix, ix->d_pts, 0, nq, k, exclude_self, true, d_idx_out, d_dist_out,
+    return tci_knn_launch(ctx, ix, nullptr, 0, nq, k, exclude_self, true, d_idx_out, d_dist_out,
                           d_count_out);
   // external queries: validate + sort by the index's grid for warp coherence
   float mn[3], mx[3];
   TC_TRY(tci_bbox(ctx, d_queries_aos, nq, mn, mx));
   float4* d_sorted = nullptr;
-  TC_TRY(tci_sort_by_grid(ctx, d_queries_aos, nq, ix->g, &d_sorted));
+  TC_TRY(tci_sort_by_grid(ctx, d_queries_aos, nq, ix->lv[0].g, &d_sorted));
   const int st = tci_knn_launch(ctx, ix, d_sorted, 0, nq, k, 0, false, d_idx_out, d_dist_out,
                                 d_count_out);
   tc_free(ctx, d_sorted);

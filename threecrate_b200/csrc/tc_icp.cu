@@ -81,19 +81,18 @@ __global__ void k_icp_init(IcpState* st, const float* init7_src, float t0, float
   st->n_valid = 0.0;
 }
 
+// target normals AoS (12 B) -> float4 (one aligned 128-bit load per match), original order
 __global__ void __launch_bounds__(kIcpBlock)
-k_gather_normals(const float* __restrict__ nrm, const float4* __restrict__ pts, uint32_t n,
-                 float4* __restrict__ out) {
+k_pad_normals(const float* __restrict__ nrm, uint32_t n, float4* __restrict__ out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t j = __float_as_uint(__ldg(&pts[i]).w);
-    const float* p = nrm + 3 * (uint64_t)j;
+    const float* p = nrm + 3 * (uint64_t)i;
     out[i] = make_float4(p[0], p[1], p[2], 0.0f);
   }
 }
 
 __global__ void __launch_bounds__(kIcpBlock)
-k_icp_correspond(GridParams g, const float4* __restrict__ tgt, const uint32_t* __restrict__ cell_start,
-                 const float4* __restrict__ tgt_nrm, const float4* __restrict__ src, uint32_t ns,
+k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
+                 const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
                  double* __restrict__ sums, uint32_t* __restrict__ match_out) {
   if (st->done) return;
@@ -110,15 +109,16 @@ k_icp_correspond(GridParams g, const float4* __restrict__ tgt, const uint32_t* _
     V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
     s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
     Best1 best;
-    grid_search(g, tgt, cell_start, s.x, s.y, s.z, best);
+    int level;
+    level_search(ls, s.x, s.y, s.z, 1u, best, level);
     bool valid = best.full();
     if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
       if (xsqrt(best.kth()) > max_dist) valid = false;
     }
     if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
     if (valid) {
-      const float4 d4 = __ldg(&tgt[best.pos]);
-      const float4 n4 = __ldg(&tgt_nrm[best.pos]);
+      const float4 d4 = __ldg(&ls.pts[level][best.pos]);
+      const float4 n4 = __ldg(&tgt_nrm[__float_as_uint(d4.w)]);
       const V3 n{n4.x, n4.y, n4.z};
       const V3 c = xcross(s, n);  // registration.rs:418
       const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
@@ -325,7 +325,7 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
     sg.ox = mn[0];
     sg.oy = mn[1];
     sg.oz = mn[2];
-    float cell = tgt->g.cell * 2.0f;
+    float cell = tgt->lv[tgt->primary].g.cell * 2.0f;
     const float emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
     if (!(cell > 0)) cell = 1.0f;
     if (emax / cell > 1000.0f) cell = emax / 1000.0f;  // <= ~2^30 cells
@@ -348,18 +348,16 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
   if (st == TC_OK) st = tc_alloc(ctx, &d_sums, kNumSums);
   IcpState h_state{};
   if (st == TC_OK) {
-    k_gather_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
-                                            ctx->sm_count * 8)),
-                       kIcpBlock, 0, ctx->stream>>>(d_tgt_normals_aos, tgt->d_pts, nt, d_nrm);
+    k_pad_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
+                                         ctx->sm_count * 8)),
+                    kIcpBlock, 0, ctx->stream>>>(d_tgt_normals_aos, nt, d_nrm);
     ctx->launches++;
     k_icp_init<<<1, 1, 0, ctx->stream>>>(d_state, nullptr, init[0], init[1], init[2], init[3],
                                          init[4], init[5], init[6]);
     ctx->launches++;
-    GridParams gp = tgt->g;
-    gp.flags = g_tc_search_flags;
+    const LevelSet ls = tgt->level_set(g_tc_search_flags);
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
-      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(gp, tgt->d_pts, tgt->d_cell_start,
-                                                            d_nrm, d_src, ns, max_corr_dist,
+      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(ls, d_nrm, d_src, ns, max_corr_dist,
                                                             d_state, d_partials, d_sums,
                                                             d_match_out);
       ctx->launches++;

@@ -77,23 +77,44 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict_
   }
 }
 
+// occupied cells -> s[8], max population -> s[9], points living in cells with population
+// <= low_thr -> s[10] (how much of the cloud is too sparse for this cell size)
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
-                                                         uint64_t n_cells,
+                                                         uint64_t n_cells, uint32_t low_thr,
                                                          uint32_t* __restrict__ s) {
-  uint32_t occ = 0, mx = 0;
+  uint32_t occ = 0, mx = 0, low = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t c = counts[i];
     occ += (c != 0);
     mx = max(mx, c);
+    low += (c <= low_thr) ? c : 0u;
   }
   for (int o = 16; o > 0; o >>= 1) {
     occ += __shfl_xor_sync(0xffffffffu, occ, o);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    low += __shfl_xor_sync(0xffffffffu, low, o);
   }
   if ((threadIdx.x & 31) == 0) {
     if (occ) atomicAdd(&s[8], occ);
     if (mx) atomicMax(&s[9], mx);
+    if (low) atomicAdd(&s[10], low);
+  }
+}
+
+// Counting-sort scatter: point i goes to cursor[cell(i)]++ as float4 (x, y, z, bits(i)).
+// `cursor` starts as a copy of cell_start.  The order INSIDE a cell is arrival order (not
+// deterministic) — nothing downstream depends on it: every selection is keyed by (d2, original
+// index) and multi-GPU shards own whole cells.
+__global__ void __launch_bounds__(kThreads) k_scatter_cells(const float* __restrict__ xyz,
+                                                            const uint32_t* __restrict__ keys,
+                                                            uint32_t n,
+                                                            uint32_t* __restrict__ cursor,
+                                                            float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = xyz + 3 * (uint64_t)i;
+    const uint32_t pos = atomicAdd(&cursor[keys[i]], 1u);
+    out[pos] = make_float4(p[0], p[1], p[2], __uint_as_float(i));
   }
 }
 
@@ -395,6 +416,75 @@ float target_population(uint32_t k_hint) {
 
 }  // namespace
 
+namespace {
+
+// histogram of `cloud` on grid g (+ keys); returns occupied / max_pop / low-population points
+int level_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t low_thr,
+                    uint32_t* d_keys, uint32_t** d_counts_out, uint32_t stats[3]) {
+  const uint64_t n = cloud->n;
+  const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
+  uint32_t* d_counts = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_counts, n_cells + 1));
+  TC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
+  k_cell_keys<0><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
+      cloud->d_xyz, (uint32_t)n, g, d_keys, d_counts);
+  TC_LAUNCHED(ctx);
+  if (stats) {
+    TC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 8, 0, 3 * sizeof(uint32_t), ctx->stream));
+    k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
+        d_counts, n_cells, low_thr, ctx->d_scratch);
+    TC_LAUNCHED(ctx);
+    TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 3 * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    stats[0] = ctx->h_scratch[8];
+    stats[1] = ctx->h_scratch[9];
+    stats[2] = ctx->h_scratch[10];
+  }
+  *d_counts_out = d_counts;
+  return TC_OK;
+}
+
+// counts -> cell_start (scan), then counting-sort scatter into the level's float4 array
+int level_finish(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t* d_keys,
+                 uint32_t* d_counts, GridLevel* lv) {
+  const uint64_t n = cloud->n;
+  lv->g = g;
+  lv->n_cells = (uint64_t)g.nx * g.ny * g.nz;
+  uint32_t* d_cursor = nullptr;
+  int st = tc_alloc(ctx, &lv->d_cell_start, lv->n_cells + 1);
+  if (st == TC_OK) st = tci_exclusive_scan_u32(ctx, d_counts, lv->d_cell_start, lv->n_cells);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_cursor, lv->n_cells + 1);
+  if (st == TC_OK) st = tc_alloc(ctx, &lv->d_pts, n);
+  if (st == TC_OK) {
+    cudaMemcpyAsync(d_cursor, lv->d_cell_start, (lv->n_cells + 1) * sizeof(uint32_t),
+                    cudaMemcpyDeviceToDevice, ctx->stream);
+    k_scatter_cells<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
+        cloud->d_xyz, d_keys, (uint32_t)n, d_cursor, lv->d_pts);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "scatter launch failed");
+  }
+  tc_free(ctx, d_cursor);
+  return st;
+}
+
+int build_extra_level(tc_context* ctx, const tc_cloud* cloud, const float mn[3], const float mx[3],
+                      float cell, uint64_t table_cap, uint32_t* d_keys, GridLevel* lv) {
+  const GridParams g = make_grid(mn, mx, cell, cloud->n, table_cap);
+  uint32_t* d_counts = nullptr;
+  TC_TRY(level_histogram(ctx, cloud, g, 0, d_keys, &d_counts, nullptr));
+  const int st = level_finish(ctx, cloud, g, d_keys, d_counts, lv);
+  tc_free(ctx, d_counts);
+  return st;
+}
+
+}  // namespace
+
+int g_tc_max_levels = kMaxLevels;
+extern "C" void tc_debug_set_max_levels(int n) {
+  g_tc_max_levels = n < 1 ? 1 : (n > kMaxLevels ? kMaxLevels : n);
+}
+
 extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint,
                               float cell_size, tc_index** out) {
   if (!ctx || !cloud || !out) return TC_INVALID_DATA;
@@ -406,10 +496,11 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   ix->cloud = cloud;
   ix->n = n;
   if (n == 0) {
-    ix->g.nx = ix->g.ny = ix->g.nz = 1;
-    ix->g.cell = 1.0f;
-    ix->g.inv = 1.0f;
-    ix->n_cells = 1;
+    ix->n_levels = 1;
+    ix->lv[0].g.nx = ix->lv[0].g.ny = ix->lv[0].g.nz = 1;
+    ix->lv[0].g.cell = 1.0f;
+    ix->lv[0].g.inv = 1.0f;
+    ix->lv[0].n_cells = 1;
     *out = ix;
     return TC_OK;
   }
@@ -430,13 +521,16 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     delete ix;
     return st;
   }
-  const uint64_t table_cap = std::min<uint64_t>(kMaxCells, std::max<uint64_t>(8 * n, 1u << 16));
+  const uint64_t table_cap = std::min<uint64_t>(kMaxCells, std::max<uint64_t>(64 * n, 1u << 20));
+  const float target = target_population(k_hint);
+  // a 3x3x3 block of surface-like data spans ~9 occupied cells: it cannot even hold k+1 points
+  // when the cells hold fewer than (k+1)/9 each
+  const uint32_t low_thr = (k_hint + 1) / 9;
 
   float cell = cell_size;
   const bool auto_cell = !(cell_size > 0.0f);
   if (auto_cell) {
     // first guess: surface-like data, area proxy = sum of the three bbox face areas
-    const float target = target_population(k_hint);
     double area = ex * ey + ey * ez + ex * ez;
     if (area <= 0) area = emax * emax;
     if (area <= 0) area = 1.0;
@@ -446,33 +540,17 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     if (emax > 0 && cell < emax * 1e-6) cell = (float)(emax * 1e-6);
   }
   GridParams g{};
+  uint32_t stats[3] = {0, 0, 0};
   const int max_trials = auto_cell ? 4 : 1;
   for (int trial = 0; trial < max_trials; ++trial) {
     g = make_grid(mn, mx, cell, n, table_cap);
     cell = g.cell;
-    const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
     tc_free(ctx, d_counts);
-    st = tc_alloc(ctx, &d_counts, n_cells + 1);
+    d_counts = nullptr;
+    st = level_histogram(ctx, cloud, g, low_thr, d_keys, &d_counts, stats);
     if (st != TC_OK) break;
-    cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream);
-    k_cell_keys<0><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
-        cloud->d_xyz, (uint32_t)n, g, d_keys, d_counts);
-    ctx->launches++;
-    cudaMemsetAsync(ctx->d_scratch + 8, 0, 2 * sizeof(uint32_t), ctx->stream);
-    k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
-        d_counts, n_cells, ctx->d_scratch);
-    ctx->launches++;
-    cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 2 * sizeof(uint32_t),
-                    cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-      st = tc_fail(ctx, TC_GPU, "index build: histogram pass failed");
-      break;
-    }
-    ix->occupied = ctx->h_scratch[8];
-    ix->max_pop = ctx->h_scratch[9];
     if (!auto_cell || trial == max_trials - 1) break;
-    const float target = target_population(k_hint);
-    const float pop = (float)n / (float)std::max(1u, ix->occupied);
+    const float pop = (float)n / (float)std::max(1u, stats[0]);
     if (pop > target * 0.7f && pop < target * 1.4f) break;
     // rescale assuming surface-like scaling (occupied cells ~ cell^-2); clamp the step
     float scale = std::sqrt(target / pop);
@@ -480,8 +558,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     float next = cell * scale;
     if (emax > 0 && next > emax) next = (float)emax;
     if (std::fabs(next - cell) < 1e-3f * cell) break;
-    // cannot refine beyond the table capacity
-    GridParams probe = make_grid(mn, mx, next, n, table_cap);
+    GridParams probe = make_grid(mn, mx, next, n, table_cap);  // table capacity may stop refinement
     if (probe.cell == cell) break;
     cell = next;
   }
@@ -491,34 +568,39 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     delete ix;
     return st;
   }
-  ix->g = g;
-  ix->n_cells = (uint64_t)g.nx * g.ny * g.nz;
-
-  // cell-range scan: counts -> cell_start (n_cells + 1 entries)
-  st = tc_alloc(ctx, &ix->d_cell_start, ix->n_cells + 1);
-  if (st == TC_OK) st = tci_exclusive_scan_u32(ctx, d_counts, ix->d_cell_start, ix->n_cells);
+  // Density skew -> extra resolutions: a 4x finer grid when some cells are far
+  // over target (dense LiDAR near field), a 4x coarser one when a visible share of the points
+  // sits in nearly empty cells (far field: ring growth would otherwise walk thousands of rows).
+  const bool want_fine = auto_cell && g_tc_max_levels > 1 && (float)stats[1] > 6.0f * target &&
+                         n > 4096;
+  const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
+                           low_thr > 0 && (double)stats[2] > 0.01 * (double)n && n > 4096;
+  GridLevel primary{};
+  primary.occupied = stats[0];
+  primary.max_pop = stats[1];
+  st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
   tc_free(ctx, d_counts);
-
-  // radix sort (key, original index) and gather into sorted float4
-  uint32_t *d_keys_alt = nullptr, *d_vals = nullptr, *d_vals_alt = nullptr;
-  uint32_t *ks = nullptr, *vs = nullptr;
-  if (st == TC_OK) st = tc_alloc(ctx, &d_keys_alt, n);
-  if (st == TC_OK) st = tc_alloc(ctx, &d_vals, n);
-  if (st == TC_OK) st = tc_alloc(ctx, &d_vals_alt, n);
-  if (st == TC_OK)
-    st = tci_radix_sort_pairs(ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n,
-                              key_bits_for(ix->n_cells), &ks, &vs);
-  if (st == TC_OK) st = tc_alloc(ctx, &ix->d_pts, n);
-  if (st == TC_OK) {
-    k_gather<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, vs, (uint32_t)n,
-                                                                       ix->d_pts);
-    ctx->launches++;
-    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "gather launch failed");
+  int nl = 0;
+  if (st == TC_OK && want_fine) {
+    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 0.25f, table_cap, d_keys, &ix->lv[nl]);
+    if (st == TC_OK && ix->lv[nl].g.cell < g.cell * 0.9f) ++nl;  // table cap may refuse to refine
+    else if (st == TC_OK) {
+      tc_free(ctx, ix->lv[nl].d_pts);
+      tc_free(ctx, ix->lv[nl].d_cell_start);
+      ix->lv[nl] = GridLevel{};
+    }
   }
+  ix->primary = nl;
+  ix->lv[nl++] = primary;
+  if (st == TC_OK && want_coarse) {
+    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 4.0f, table_cap, d_keys, &ix->lv[nl]);
+    if (st == TC_OK) ++nl;
+  }
+  ix->n_levels = nl;
+  // finer cells nest inside primary cells (same origin, edge / 4): their population is bounded by
+  // the primary maximum; the slack covers points that f32 rounding puts across a cell face
+  for (int i = 0; i < nl; ++i) ix->lv[i].max_pop_bound = 2 * primary.max_pop + 32;
   tc_free(ctx, d_keys);
-  tc_free(ctx, d_keys_alt);
-  tc_free(ctx, d_vals);
-  tc_free(ctx, d_vals_alt);
   if (st != TC_OK) {
     tc_index_free(ix);
     return st;
@@ -529,25 +611,29 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
 
 extern "C" void tc_index_free(tc_index* ix) {
   if (!ix) return;
-  tc_free(ix->ctx, ix->d_pts);
-  tc_free(ix->ctx, ix->d_cell_start);
+  for (int i = 0; i < kMaxLevels; ++i) {
+    tc_free(ix->ctx, ix->lv[i].d_pts);
+    tc_free(ix->ctx, ix->lv[i].d_cell_start);
+  }
   delete ix;
 }
 
 extern "C" int tc_index_get_info(const tc_index* ix, tc_index_info* out) {
   if (!ix || !out) return TC_INVALID_DATA;
+  const GridLevel& p = ix->lv[ix->primary];
   out->n_points = ix->n;
-  out->n_cells = ix->n_cells;
-  out->dims[0] = ix->g.nx;
-  out->dims[1] = ix->g.ny;
-  out->dims[2] = ix->g.nz;
-  out->cell_size = ix->g.cell;
+  out->n_cells = p.n_cells;
+  out->dims[0] = p.g.nx;
+  out->dims[1] = p.g.ny;
+  out->dims[2] = p.g.nz;
+  out->cell_size = p.g.cell;
   for (int a = 0; a < 3; ++a) {
     out->bbox_min[a] = ix->bbox_min[a];
     out->bbox_max[a] = ix->bbox_max[a];
   }
-  out->occupied_cells = ix->occupied;
-  out->max_cell_population = ix->max_pop;
+  out->occupied_cells = p.occupied;
+  out->max_cell_population = p.max_pop;
+  out->n_levels = (uint32_t)ix->n_levels;
   return TC_OK;
 }
 

@@ -41,16 +41,43 @@ struct GridParams {
   int flags;            // search variant bits (see tc_search.cuh)
 };
 
+// One resolution of the index: a complete uniform grid over all points.
+constexpr int kMaxLevels = 3;
+struct GridLevel {
+  GridParams g{};
+  float4* d_pts = nullptr;           // sorted by cell: x, y, z, bits(original index)
+  uint32_t* d_cell_start = nullptr;  // n_cells + 1
+  uint64_t n_cells = 0;
+  uint32_t occupied = 0, max_pop = 0;
+  uint32_t max_pop_bound = 0;        // >= the largest cell population (shard launch slack)
+};
+// What the search kernels receive (by value): the levels from fine to coarse.
+struct LevelSet {
+  int n;
+  GridParams g[kMaxLevels];
+  const float4* pts[kMaxLevels];
+  const uint32_t* cs[kMaxLevels];
+};
+
 struct tc_index {
   tc_context* ctx = nullptr;
   const tc_cloud* cloud = nullptr;  // borrowed; must outlive the index
   uint64_t n = 0;
-  GridParams g{};
   float bbox_min[3]{}, bbox_max[3]{};
-  uint64_t n_cells = 0;
-  float4* d_pts = nullptr;          // sorted by cell: x, y, z, bits(original index)
-  uint32_t* d_cell_start = nullptr; // n_cells + 1
-  uint32_t occupied = 0, max_pop = 0;
+  int n_levels = 0;
+  int primary = 0;                  // the level built for the requested / automatic cell size
+  GridLevel lv[kMaxLevels];         // fine -> coarse
+  LevelSet level_set(int flags) const {
+    LevelSet s{};
+    s.n = n_levels;
+    for (int i = 0; i < n_levels; ++i) {
+      s.g[i] = lv[i].g;
+      s.g[i].flags = flags;
+      s.pts[i] = lv[i].d_pts;
+      s.cs[i] = lv[i].d_cell_start;
+    }
+    return s;
+  }
 };
 
 struct tc_comm;  // tc_comm.cu

@@ -27,13 +27,15 @@ using namespace tcs;
 //           (a 4-instruction append, so lanes that accept different candidates cost little)
 //   rank    uniform loop over the n members: slot = #{v[i] < d2}; s_b[slot] = position
 template <int L>
-__device__ __forceinline__ int select_two_pass(const GridParams& g, const float4* __restrict__ pts,
-                                               const uint32_t* __restrict__ cell_start, float qx,
-                                               float qy, float qz, uint32_t need,
-                                               uint32_t (*s_a)[kBlock], uint32_t (*s_b)[kBlock]) {
+__device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, float qy, float qz,
+                                               uint32_t need, uint32_t (*s_a)[kBlock],
+                                               uint32_t (*s_b)[kBlock], int& level) {
   SelF<L> sel;
   sel.pad = L - (int)need;
-  const int R = grid_search(g, pts, cell_start, qx, qy, qz, sel);
+  const int R = level_search(ls, qx, qy, qz, need, sel, level);
+  const GridParams& g = ls.g[level];
+  const float4* __restrict__ pts = ls.pts[level];
+  const uint32_t* __restrict__ cell_start = ls.cs[level];
   const float tau = sel.kth();  // +inf when fewer than `need` points exist: everything is kept
   // bit-equal real entries would collide in the rank placement -> exact chain kernel instead
   bool tie = false;
@@ -64,6 +66,20 @@ __device__ __forceinline__ int select_two_pass(const GridParams& g, const float4
     s_b[rank][threadIdx.x] = j;
   }
   return (int)n;
+}
+
+// Shard ownership (multi-GPU): the query at sorted position p belongs to the shard that contains
+// the FIRST position of its level-0 cell, so shards own whole cells and the assignment does not
+// depend on the (arbitrary) order of points inside a cell.
+__device__ __forceinline__ bool owns_query(const LevelSet& ls, const float4& q, uint32_t begin,
+                                           uint32_t end) {
+  const GridParams& g = ls.g[0];
+  float u;
+  const int cx = cell_coord(q.x, g.ox, g.inv, g.nx, u);
+  const int cy = cell_coord(q.y, g.oy, g.inv, g.ny, u);
+  const int cz = cell_coord(q.z, g.oz, g.inv, g.nz, u);
+  const uint32_t first = __ldg(&ls.cs[0][cell_id(g, cx, cy, cz)]);
+  return first >= begin && first < end;
 }
 
 // ---------------------------------------------------------------------------------- kNN kernel
@@ -157,18 +173,18 @@ __device__ __forceinline__ void knn_emit(const KS& keys, uint32_t qid, uint32_t 
 // tie-overflow fallback of the two-pass kernels), grid-stride.
 template <int K>
 __global__ void __launch_bounds__(kBlock)
-k_knn(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-      const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end, uint32_t k,
-      int drop_self, uint32_t* __restrict__ idx_out, float* __restrict__ dist_out,
-      uint32_t* __restrict__ count_out, const uint32_t* __restrict__ list,
-      const uint32_t* __restrict__ list_count) {
+k_knn(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end,
+      uint32_t k, uint32_t need, int drop_self, uint32_t* __restrict__ idx_out,
+      float* __restrict__ dist_out, uint32_t* __restrict__ count_out,
+      const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
   const uint32_t total = list ? *list_count : (q_end - q_begin);
   for (uint32_t t = blockIdx.x * kBlock + threadIdx.x; t < total; t += gridDim.x * kBlock) {
     const uint32_t qi = list ? list[t] : q_begin + t;
     const float4 q = __ldg(&queries[qi]);
     const uint32_t qid = __float_as_uint(q.w);  // original query index = output row
     TopK<K> tk;
-    grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
+    int level;
+    level_search(ls, q.x, q.y, q.z, need, tk, level);
     knn_emit(RegKeys<K>{tk.key, nullptr}, qid, k, drop_self, idx_out, dist_out, count_out);
   }
 }
@@ -178,22 +194,23 @@ k_knn(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__
 // single u64 bitonic sort then orders.  More than L members (ties) -> fallback list.
 template <int L>
 __global__ void __launch_bounds__(kBlock)
-k_knn2(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-       const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end, uint32_t k,
-       uint32_t need, int drop_self, uint32_t* __restrict__ idx_out, float* __restrict__ dist_out,
-       uint32_t* __restrict__ count_out, uint32_t* __restrict__ fb_list,
-       uint32_t* __restrict__ fb_count) {
+k_knn2(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end,
+       uint32_t k, uint32_t need, int drop_self, uint32_t* __restrict__ idx_out,
+       float* __restrict__ dist_out, uint32_t* __restrict__ count_out,
+       uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
   __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
   const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
   if (qi >= q_end) return;
   const float4 q = __ldg(&queries[qi]);
   const uint32_t qid = __float_as_uint(q.w);
-  const int n = select_two_pass<L>(g, pts, cell_start, q.x, q.y, q.z, need, s_a, s_b);
+  int level;
+  const int n = select_two_pass<L>(ls, q.x, q.y, q.z, need, s_a, s_b, level);
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
   }
-  knn_emit(SortedPos{s_b, n, pts, q.x, q.y, q.z}, qid, k, drop_self, idx_out, dist_out, count_out);
+  knn_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, qid, k, drop_self, idx_out, dist_out,
+           count_out);
 }
 
 // ------------------------------------------------------------------------- symmetric 3x3 eigen
@@ -350,49 +367,52 @@ __device__ __forceinline__ void normals_emit(const KS& keys, const float4 q, uin
 
 template <int K>
 __global__ void __launch_bounds__(kBlock)
-k_normals(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-          const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end, uint32_t k, int orient,
-          float vpx, float vpy, float vpz, float* __restrict__ out,
-          const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
-          uint32_t* __restrict__ dbg) {
+k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end,
+          uint32_t own_begin, uint32_t own_end, uint32_t k, int orient, float vpx, float vpy,
+          float vpz, float* __restrict__ out, const uint32_t* __restrict__ list,
+          const uint32_t* __restrict__ list_count, uint32_t* __restrict__ dbg) {
   const uint32_t total = list ? *list_count : (q_end - q_begin);
   for (uint32_t t = blockIdx.x * kBlock + threadIdx.x; t < total; t += gridDim.x * kBlock) {
     const uint32_t qi = list ? list[t] : q_begin + t;
-    const float4 q = __ldg(&pts[qi]);
+    const float4 q = __ldg(&ls.pts[0][qi]);
+    if (!list && own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) continue;
     const uint32_t qid = __float_as_uint(q.w);
     const long long t0 = dbg ? clock64() : 0;
     TopK<K> tk;
-    const int R = grid_search(g, pts, cell_start, q.x, q.y, q.z, tk);
+    int level;
+    const int R = level_search(ls, q.x, q.y, q.z, k + 1, tk, level);
     normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
     if (dbg) {  // per-query cycles and final block radius (tools/kbench.py --dbg)
       dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
-      dbg[2 * (size_t)qid + 1] = (uint32_t)R;
+      dbg[2 * (size_t)qid + 1] = (uint32_t)R | ((uint32_t)level << 16);
     }
   }
 }
 
 template <int L>
 __global__ void __launch_bounds__(kBlock)
-k_normals2(GridParams g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-           const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end, uint32_t k, int orient,
-           float vpx, float vpy, float vpz, float* __restrict__ out,
+k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, uint32_t own_end,
+           uint32_t k, int orient, float vpx, float vpy, float vpz, float* __restrict__ out,
            uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
            uint32_t* __restrict__ dbg) {
   __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
   const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
   if (qi >= q_end) return;
-  const float4 q = __ldg(&pts[qi]);
+  const float4 q = __ldg(&ls.pts[0][qi]);
+  if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   const uint32_t qid = __float_as_uint(q.w);
   const long long t0 = dbg ? clock64() : 0;
-  const int n = select_two_pass<L>(g, pts, cell_start, q.x, q.y, q.z, k + 1, s_a, s_b);
+  int level;
+  const int n = select_two_pass<L>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level);
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
   }
-  normals_emit(SortedPos{s_b, n, pts, q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz, out);
+  normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
+               out);
   if (dbg) {
     dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
-    dbg[2 * (size_t)qid + 1] = (uint32_t)n;
+    dbg[2 * (size_t)qid + 1] = (uint32_t)n | ((uint32_t)level << 16);
   }
 }
 
@@ -443,79 +463,81 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
     return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 64 incl. self)");
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
-  GridParams gp = ix->g;
-  gp.flags = g_tc_search_flags;
-  const bool two_pass = (gp.flags & 4) && need <= 32 && need >= 2;
+  int flags = g_tc_search_flags;
+  const bool two_pass = (flags & 4) && need <= 32 && need >= 2;
+  if (two_pass) flags |= 2;  // pruning is always worth it with the batch scan
+  const LevelSet ls = ix->level_set(flags);
+  if (self_query) d_queries_sorted = ix->lv[0].d_pts;
   if (!two_pass) {
     TC_DISPATCH_K(sz, (k_knn<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                          gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, (uint32_t)q_begin,
-                          (uint32_t)q_end, k, drop_self, d_idx_out, d_dist_out, d_count_out,
-                          nullptr, nullptr)));
+                          ls, d_queries_sorted, (uint32_t)q_begin, (uint32_t)q_end, k, need,
+                          drop_self, d_idx_out, d_dist_out, d_count_out, nullptr, nullptr)));
     TC_LAUNCHED(ctx);
     return TC_OK;
   }
   uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions that overflowed on ties
   TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
-  gp.flags |= 2;  // row pruning is always worth it here
   if (need <= 16)
-    k_knn2<16><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start, d_queries_sorted,
-                                                 (uint32_t)q_begin, (uint32_t)q_end, k, need,
-                                                 drop_self, d_idx_out, d_dist_out, d_count_out,
-                                                 d_fb + 1, d_fb);
+    k_knn2<16><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,
+                                                 (uint32_t)q_end, k, need, drop_self, d_idx_out,
+                                                 d_dist_out, d_count_out, d_fb + 1, d_fb);
   else
-    k_knn2<32><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start, d_queries_sorted,
-                                                 (uint32_t)q_begin, (uint32_t)q_end, k, need,
-                                                 drop_self, d_idx_out, d_dist_out, d_count_out,
-                                                 d_fb + 1, d_fb);
+    k_knn2<32><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,
+                                                 (uint32_t)q_end, k, need, drop_self, d_idx_out,
+                                                 d_dist_out, d_count_out, d_fb + 1, d_fb);
   TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_knn<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
-                        gp, ix->d_pts, ix->d_cell_start, d_queries_sorted, 0u, 0u, k, drop_self,
-                        d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)));
+                        ls, d_queries_sorted, 0u, 0u, k, need, drop_self, d_idx_out, d_dist_out,
+                        d_count_out, d_fb + 1, d_fb)));
   TC_LAUNCHED(ctx);
   tc_free(ctx, d_fb);
   return TC_OK;
 }
 
+// Normals for the shard [q_begin, q_end) of the level-0 sorted order.  Shards own whole cells
+// (owns_query), so the launch covers up to max_pop extra positions past q_end.
 int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orient,
                        const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos) {
   if (q_end <= q_begin) return TC_OK;
   const int sz = pick_size(k + 1);
   if (sz == 0)
     return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 63 for normals)");
+  const bool whole = (q_begin == 0 && q_end >= ix->n);
+  const uint32_t own_begin = (uint32_t)q_begin;
+  const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
+  if (!whole) q_end = std::min<uint64_t>(ix->n, q_end + ix->lv[0].max_pop_bound);
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
-  GridParams gp = ix->g;
-  gp.flags = g_tc_search_flags;
-  const bool two_pass = (gp.flags & 4) && k + 1 <= 32;
+  int flags = g_tc_search_flags;
+  const bool two_pass = (flags & 4) && k + 1 <= 32;
+  if (two_pass) flags |= 2;
+  const LevelSet ls = ix->level_set(flags);
   if (!two_pass) {
     TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
-                          gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, (uint32_t)q_begin,
-                          (uint32_t)q_end, k, orient, vp[0], vp[1], vp[2], d_out_aos, nullptr,
-                          nullptr, g_tc_dbg)));
+                          ls, ix->cloud->d_xyz, (uint32_t)q_begin, (uint32_t)q_end, own_begin,
+                          own_end, k, orient, vp[0], vp[1], vp[2], d_out_aos, nullptr, nullptr,
+                          g_tc_dbg)));
     TC_LAUNCHED(ctx);
     return TC_OK;
   }
   uint32_t* d_fb = nullptr;
   TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
-  gp.flags |= 2;
   if (k + 1 <= 16)
-    k_normals2<16><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start,
-                                                     ix->cloud->d_xyz, (uint32_t)q_begin,
-                                                     (uint32_t)q_end, k, orient, vp[0], vp[1],
+    k_normals2<16><<<grid, kBlock, 0, ctx->stream>>>(ls, (uint32_t)q_begin, (uint32_t)q_end,
+                                                     own_begin, own_end, k, orient, vp[0], vp[1],
                                                      vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
   else
-    k_normals2<32><<<grid, kBlock, 0, ctx->stream>>>(gp, ix->d_pts, ix->d_cell_start,
-                                                     ix->cloud->d_xyz, (uint32_t)q_begin,
-                                                     (uint32_t)q_end, k, orient, vp[0], vp[1],
+    k_normals2<32><<<grid, kBlock, 0, ctx->stream>>>(ls, (uint32_t)q_begin, (uint32_t)q_end,
+                                                     own_begin, own_end, k, orient, vp[0], vp[1],
                                                      vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
   TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
-                        gp, ix->d_pts, ix->d_cell_start, ix->cloud->d_xyz, 0u, 0u, k, orient, vp[0],
-                        vp[1], vp[2], d_out_aos, d_fb + 1, d_fb, nullptr)));
+                        ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],
+                        d_out_aos, d_fb + 1, d_fb, nullptr)));
   TC_LAUNCHED(ctx);
   tc_free(ctx, d_fb);
   return TC_OK;

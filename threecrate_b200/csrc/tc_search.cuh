@@ -229,10 +229,12 @@ __device__ __forceinline__ float row_gap(int d, float f) {
 
 // Exact nearest-neighbour search for one query; Acc is TopK<K> or Best1.
 // flags: bit 0 deferred insertion (TopK), bit 1 prune rows that cannot beat the K-th distance.
+// Searches blocks of radius 1, 2, ... ; `done` tells whether the result is final (otherwise the
+// caller escalates to a coarser level: only while the block does not even hold K points).
 template <class Acc>
 __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __restrict__ pts,
                                            const uint32_t* __restrict__ cell_start, float qx,
-                                           float qy, float qz, Acc& tk) {
+                                           float qy, float qz, Acc& tk, int max_R, bool& done) {
   tk.init();
   const int flags = g.flags;
   float ux, uy, uz;
@@ -303,11 +305,46 @@ __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __
       }
     }
     const float b = ring_bound(g, R, cx, cy, cz, fx, fy, fz, mx, my, mz);
+    done = true;
     if (b == INFINITY) break;  // the searched block already covers the whole grid
     if (tk.full() && tk.kth() < b * b * 0.99999f) break;
+    done = false;
+    // escalate to a coarser level only while the block does not even hold K points (sparse
+    // neighbourhood); a full list that is not yet provably final needs just another ring here
+    if (R >= max_R && !tk.full()) break;
     Rp = R;
     R = tk.full() ? R + 1 : 2 * R;
   }
+  return R;
+}
+
+// Multi-resolution driver.  Start at the finest level whose own cell holds at least 0.4 `need`
+// points (two table loads per level), search its 3x3x3 block, and restart on the next coarser
+// level while that block does not even hold `need` points; only the coarsest level keeps
+// doubling its radius when starved.
+template <class Acc>
+__device__ __forceinline__ int level_search(const LevelSet& ls, float qx, float qy, float qz,
+                                            uint32_t need, Acc& tk, int& level) {
+  int l = 0;
+  for (; l < ls.n - 1; ++l) {
+    const GridParams& g = ls.g[l];
+    float u;
+    const int cx = cell_coord(qx, g.ox, g.inv, g.nx, u);
+    const int cy = cell_coord(qy, g.oy, g.inv, g.ny, u);
+    const int cz = cell_coord(qz, g.oz, g.inv, g.nz, u);
+    const uint32_t c = cell_id(g, cx, cy, cz);
+    const uint32_t pop = __ldg(&ls.cs[l][c + 1]) - __ldg(&ls.cs[l][c]);
+    if (pop * 5u >= need * 2u) break;
+  }
+  int R;
+  while (true) {
+    bool done;
+    R = grid_search(ls.g[l], ls.pts[l], ls.cs[l], qx, qy, qz, tk, (l == ls.n - 1) ? (1 << 30) : 1,
+                    done);
+    if (done) break;
+    ++l;
+  }
+  level = l;
   return R;
 }
 
