@@ -94,24 +94,48 @@ __global__ void __launch_bounds__(kIcpBlock)
 k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
                  const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
-                 double* __restrict__ sums, uint32_t* __restrict__ match_out) {
+                 double* __restrict__ sums, uint32_t* __restrict__ match_out,
+                 uint32_t* __restrict__ prev) {
   if (st->done) return;
   float T[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) T[i] = st->T[i];
-  double acc[kNumSums];
+  // Per-thread partials in f32: the products a_i a_j are f32 in the reference too
+  // (registration.rs:426-427) and a thread only sums a handful of points; everything across
+  // threads (warp, block, grid) is reduced in f64.
+  float acc[kNumSums];
 #pragma unroll
-  for (int i = 0; i < kNumSums; ++i) acc[i] = 0.0;
+  for (int i = 0; i < kNumSums; ++i) acc[i] = 0.0f;
 
   for (uint32_t i = blockIdx.x * kIcpBlock + threadIdx.x; i < ns; i += gridDim.x * kIcpBlock) {
     const float4 s4 = __ldg(&src[i]);
     // current_transform * p  (registration.rs:540-544)
     V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
     s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
+    // Seed the search with last iteration's match (level << 30 | sorted position): the pose moves
+    // little between iterations, so this candidate is almost always the answer again and bounds
+    // the search to the one or two cells around the query.  Exactness is unaffected.
     Best1 best;
-    int level;
-    level_search(ls, s.x, s.y, s.z, 1u, best, level);
+    int level, start = -1;
+    const uint32_t seed = prev ? prev[i] : 0xFFFFFFFFu;
+    if (seed != 0xFFFFFFFFu) {
+      start = (int)(seed >> 30);
+      best.pos = seed & 0x3FFFFFFFu;
+      const float4 c = __ldg(&ls.pts[start][best.pos]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, s.x, s.y, s.z);
+      best.key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+      best.seeded = true;
+    }
+    if (best.seeded) {
+      // box query around the seed distance: usually one or two rows of one or two cells
+      level = start;
+      box_visit(ls.g[level], ls.cs[level], s.x, s.y, s.z, best.kth(),
+                [&](uint32_t lo, uint32_t hi) { best.scan(ls.pts[level], lo, hi, s.x, s.y, s.z, 0); });
+    } else {
+      level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
+    }
     bool valid = best.full();
+    if (prev) prev[i] = valid ? (((uint32_t)level << 30) | best.pos) : 0xFFFFFFFFu;
     if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
       if (xsqrt(best.kth()) > max_dist) valid = false;
     }
@@ -123,16 +147,16 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
       const V3 c = xcross(s, n);  // registration.rs:418
       const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
       const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
-      const double a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
-      const double bd = b;
+      const float a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int cc = r; cc < 6; ++cc) acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += a[r] * a[cc];
+        for (int cc = r; cc < 6; ++cc)
+          acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += xmul(a[r], a[cc]);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * bd;
-      acc[27] += bd * bd;
-      acc[28] += 1.0;
+      for (int r = 0; r < 6; ++r) acc[21 + r] += xmul(a[r], b);
+      acc[27] += xmul(b, b);
+      acc[28] += 1.0f;
     }
   }
   // warp-shuffle tree, then one row per warp in shared memory
@@ -140,7 +164,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < kNumSums; ++i) {
-    double v = acc[i];
+    double v = (double)acc[i];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sm[warp][i] = v;
   }
@@ -340,10 +364,15 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
   const int grid = std::max(1, std::min((int)((ns + kIcpBlock - 1) / kIcpBlock), ctx->sm_count * 4));
 
   float4* d_nrm = nullptr;
+  uint32_t* d_prev = nullptr;
   IcpState* d_state = nullptr;
   double *d_partials = nullptr, *d_sums = nullptr;
   int st = tc_alloc(ctx, &d_nrm, nt);
   if (st == TC_OK) st = tc_alloc(ctx, &d_state, 1);
+  if (st == TC_OK && nt < (1u << 30) && ns > 0) {
+    st = tc_alloc(ctx, &d_prev, ns);
+    if (st == TC_OK) cudaMemsetAsync(d_prev, 0xFF, (size_t)ns * sizeof(uint32_t), ctx->stream);
+  }
   if (st == TC_OK) st = tc_alloc(ctx, &d_partials, (uint64_t)grid * kNumSums);
   if (st == TC_OK) st = tc_alloc(ctx, &d_sums, kNumSums);
   IcpState h_state{};
@@ -359,7 +388,7 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
       k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(ls, d_nrm, d_src, ns, max_corr_dist,
                                                             d_state, d_partials, d_sums,
-                                                            d_match_out);
+                                                            d_match_out, d_prev);
       ctx->launches++;
       if (comm) st = tci_comm_allreduce(comm, d_sums, kNumSums);
       k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
@@ -376,6 +405,7 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
     }
   }
   tc_free(ctx, d_src);
+  tc_free(ctx, d_prev);
   tc_free(ctx, d_nrm);
   tc_free(ctx, d_state);
   tc_free(ctx, d_partials);

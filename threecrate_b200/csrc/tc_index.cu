@@ -409,7 +409,7 @@ float target_population(uint32_t k_hint) {
   // points per occupied cell aimed for: ring-1 (3x3x3) search is exact when the k-th neighbour
   // lies within one cell edge; ~0.55 (k+1) per cell keeps that true for surface-like data.
   float t = 0.55f * (float)(k_hint + 1);
-  if (t < 2.0f) t = 2.0f;
+  if (t < 4.0f) t = 4.0f;  // 1-NN (ICP): ~4 per cell measured best (fewer rows, still few candidates)
   if (t > 48.0f) t = 48.0f;
   return t;
 }

@@ -197,10 +197,13 @@ __device__ __forceinline__ float ring_bound(const GridParams& g, int R, int cx, 
 }
 
 // 1-NN accumulator (ICP correspondences): best (d2, original index) key plus its sorted position.
+// `seeded`: key/pos were preset from a known candidate (the previous ICP iteration's match).
 struct Best1 {
   uint64_t key;
   uint32_t pos;
+  bool seeded = false;
   __device__ __forceinline__ void init() {
+    if (seeded) return;
     key = kEmpty;
     pos = 0;
   }
@@ -324,9 +327,10 @@ __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __
 // doubling its radius when starved.
 template <class Acc>
 __device__ __forceinline__ int level_search(const LevelSet& ls, float qx, float qy, float qz,
-                                            uint32_t need, Acc& tk, int& level) {
-  int l = 0;
-  for (; l < ls.n - 1; ++l) {
+                                            uint32_t need, Acc& tk, int& level,
+                                            int start_level = -1) {
+  int l = start_level >= 0 ? start_level : 0;
+  for (; start_level < 0 && l < ls.n - 1; ++l) {
     const GridParams& g = ls.g[l];
     float u;
     const int cx = cell_coord(qx, g.ox, g.inv, g.nx, u);
@@ -385,6 +389,39 @@ __device__ __forceinline__ void grid_visit(const GridParams& g, const uint32_t* 
       f(lo, hi);
     }
   }
+}
+
+// Box query: hand `f` the candidate range of every row of cells that can hold a point within
+// squared distance r2 of the query.  Exact by monotonicity: the f32 cell-coordinate expression
+// is non-decreasing in the coordinate, so a point with |p - q| <= r on an axis has its cell
+// coordinate within [cell(q - r), cell(q + r)] (r is inflated to absorb the rounding of the
+// square root and of q -+ r).  Used where a distance bound is already known: pass 2 of the
+// two-pass selection (r2 = the final K-th d2) and ICP correspondences seeded with the previous
+// iteration's match.  `r2` may shrink while iterating (f returns the current bound).
+template <class F>
+__device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* __restrict__ cell_start,
+                                          float qx, float qy, float qz, float r2, F&& f) {
+  if (!(r2 < INFINITY)) {  // unbounded: every cell
+    for (int z = 0; z < g.nz; ++z)
+      for (int y = 0; y < g.ny; ++y) {
+        const uint32_t row = cell_id(g, 0, y, z);
+        f(__ldg(&cell_start[row]), __ldg(&cell_start[row + g.nx]));
+      }
+    return;
+  }
+  const float r = xsqrt(r2) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell) +
+                  1e-30f;
+  float u;
+  const int xa = cell_coord(qx - r, g.ox, g.inv, g.nx, u), xb = cell_coord(qx + r, g.ox, g.inv, g.nx, u);
+  const int ya = cell_coord(qy - r, g.oy, g.inv, g.ny, u), yb = cell_coord(qy + r, g.oy, g.inv, g.ny, u);
+  const int za = cell_coord(qz - r, g.oz, g.inv, g.nz, u), zb = cell_coord(qz + r, g.oz, g.inv, g.nz, u);
+  for (int z = za; z <= zb; ++z)
+    for (int y = ya; y <= yb; ++y) {
+      const uint32_t row = cell_id(g, 0, y, z);
+      const uint32_t lo = __ldg(&cell_start[row + xa]);
+      const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
+      f(lo, hi);
+    }
 }
 
 }  // namespace tcs
