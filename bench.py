@@ -67,7 +67,8 @@ class ClockSampler:
             self.path = f.name
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                 "100", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+                 "20", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)  # let the sampler come up before the timed region starts
         except Exception:
             self.proc = None
 
@@ -136,7 +137,7 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4 extra workloads")
@@ -217,14 +218,14 @@ def main():
             record.append((e0, e1, e2))
         return index
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         flush_l2()
         step_resident().free()
     ctx.synchronize()
     barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = ctx.launch_count
     evs = []
     t_wall0 = time.perf_counter()
@@ -342,8 +343,8 @@ def bench_c4(args, tc, synth, ctx, ext, rank, world, barrier, max_over_ranks, pe
     pts = synth.terrain(n, 100.0 * (n / 10_000_000) ** 0.5, seed=4, noise=0.002)
     cloud = tc.DeviceCloud(pts, ctx)
     d_out = ctx.alloc(n * 24)
-    lo = rank * n // world
-    hi = (rank + 1) * n // world
+    from threecrate_b200.sharding import shard_range
+    lo, hi = shard_range(rank, world, n)
     steps, warm = 3, 2
     res = []
     for it in range(warm + steps):
@@ -387,8 +388,8 @@ def bench_c3(args, tc, synth, ctx, ext, rank, world, barrier, max_over_ranks, pe
     29-scalar all-reduce per iteration at N > 1."""
     n = args.c3_points
     src, tgt, nrm, T = synth.scan_pair(n, half_extent=50.0 * (n / 1_000_000) ** 0.5)
-    lo = rank * n // world
-    hi = (rank + 1) * n // world
+    from threecrate_b200.sharding import shard_range
+    lo, hi = shard_range(rank, world, n)
     comm = None
     if world > 1:
         ids = [tc.Comm.unique_id(ctx) if rank == 0 else None]
