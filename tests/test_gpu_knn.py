@@ -135,3 +135,34 @@ def test_full_size_properties_1m():
     assert np.array_equal(np.sqrt(d2.astype(np.float32)), dist[sel])
     info = index.info()
     assert info["n_points"] == len(pts) and info["occupied_cells"] > 0
+
+
+def test_radius_search_matches_reference(orc):
+    """KdTree::find_radius_neighbors (nearest_neighbor.rs:254-298): inclusive d2 <= r2, ascending."""
+    rng = np.random.default_rng(31)
+    pts = rng.uniform(-5, 5, (30000, 3)).astype(np.float32)
+    t = tc.KdTree(pts)
+    o = orc.OracleKdTree(pts)
+    for q, r in [(pts[17], 0.6), ([0.1, 0.2, 0.3], 1.1), ([7.0, 7.0, 7.0], 4.0), ([0, 0, 0], 0.05),
+                 ([100, 0, 0], 1.0)]:
+        gi, gd = t.find_radius_neighbors(q, r)
+        oi, od = o.find_radius_neighbors(q, r)
+        assert len(gi) == len(oi)
+        assert np.array_equal(np.sort(gi), np.sort(oi.astype(np.uint32)))
+        assert np.array_equal(gd, np.sort(od))  # same distances, ascending
+        assert np.all(np.diff(gd) >= 0) and np.all(gd <= np.float32(r) + 1e-7)
+    # radius <= 0 and the reference's cube fixture (point_cloud_ops.rs:186-203 shape)
+    assert len(t.find_radius_neighbors([0, 0, 0], 0.0)[0]) == 0
+    assert len(t.find_radius_neighbors([0, 0, 0], -1.0)[0]) == 0
+    cube = tc.KdTree(synth.cube8())
+    idx, dist = cube.find_radius_neighbors([0, 0, 0], 1.0)
+    assert sorted(idx.tolist()) == [0, 1, 2, 3]  # boundary points included
+
+
+def test_kitti_strided_upload_matches_packed():
+    """KITTI .bin records (x,y,z,intensity; stride 16, threecrate-io/src/lidar.rs:310-345) uploaded
+    raw and de-interleaved on the device give the same cloud as the packed path."""
+    raw = synth.kitti_frame(with_intensity=True)
+    a = tc.GridIndex(tc.DeviceCloud(raw, stride_bytes=16), k_hint=16).estimate_normals(16)
+    b = tc.estimate_normals(np.ascontiguousarray(raw[:, :3]), 16)
+    assert np.array_equal(a, b)

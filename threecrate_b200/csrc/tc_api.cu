@@ -1,5 +1,7 @@
 // tc_api.cu — C ABI glue: context, device-resident cloud, and the host-buffer entry points that
 // mirror the reference's public functions (see include/threecrate_cuda.h for the citations).
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -309,9 +311,53 @@ extern "C" int tc_radius_search(tc_context* ctx, const tc_index* ix, const float
                                 float radius, uint32_t* idx_out, float* dist_out, uint64_t capacity,
                                 uint64_t* n_found) {
   TC_ENTER(ctx);
-  (void)ix; (void)query; (void)radius; (void)idx_out; (void)dist_out; (void)capacity;
-  if (n_found) *n_found = 0;
-  return tc_fail(ctx, TC_GPU, "tc_radius_search: not implemented on the device path yet");
+  if (!ix || !query || !n_found) return TC_INVALID_DATA;
+  *n_found = 0;
+  if (!(radius > 0.0f) || ix->n == 0) return TC_OK;  // nearest_neighbor.rs:255-257
+  for (int a = 0; a < 3; ++a)
+    if (!std::isfinite(query[a])) return tc_fail(ctx, TC_INVALID_DATA, "query must be finite");
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(ix->n, 0xFFFFFFFEull);
+  uint32_t *d_idx = nullptr, *d_cnt = nullptr;
+  float* d_d2 = nullptr;
+  int st = tc_alloc(ctx, &d_idx, cap);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_d2, cap);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_cnt, 1);
+  std::vector<uint32_t> hi;
+  std::vector<float> hd;
+  uint32_t found = 0;
+  if (st == TC_OK) {
+    cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), ctx->stream);
+    st = tci_radius_search_launch(ctx, ix, query, radius, d_idx, d_d2, cap, d_cnt);
+  }
+  if (st == TC_OK) {
+    cudaError_t e = cudaMemcpyAsync(&found, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && found > 0) {
+      hi.resize(found);
+      hd.resize(found);
+      e = cudaMemcpyAsync(hi.data(), d_idx, found * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(hd.data(), d_d2, found * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) st = tc_fail(ctx, TC_GPU, std::string("radius search: ") + cudaGetErrorString(e));
+  }
+  tc_free(ctx, d_idx);
+  tc_free(ctx, d_d2);
+  tc_free(ctx, d_cnt);
+  if (st != TC_OK) return st;
+  // order the hits ascending by (d2, index) — host-side formatting of the device result
+  std::vector<uint32_t> order(found);
+  for (uint32_t i = 0; i < found; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return hd[a] < hd[b] || (hd[a] == hd[b] && hi[a] < hi[b]);
+  });
+  *n_found = found;
+  for (uint64_t i = 0; i < found && i < capacity; ++i) {
+    if (idx_out) idx_out[i] = hi[order[i]];
+    if (dist_out) dist_out[i] = std::sqrt(hd[order[i]]);
+  }
+  return TC_OK;
 }
 
 // ------------------------------------------------------------------------------------ normals
@@ -339,8 +385,6 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
   if (!ix) return TC_INVALID_DATA;
   if (ix->n == 0) return TC_OK;  // empty -> Ok(empty), checked before k (normals.rs:261-263)
   if (k < 3) return tc_fail(ctx, TC_INVALID_DATA, "k_neighbors must be at least 3");
-  if (radius >= 0.0f)
-    return tc_fail(ctx, TC_GPU, "radius-mode normals are not implemented on the device path yet");
   if (!d_out_aos) return TC_INVALID_DATA;
   if (shard_end > ix->n) shard_end = ix->n;
   float vp[3];
@@ -350,6 +394,11 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
     vp[2] = viewpoint3[2];
   } else {
     default_viewpoint(ix->bbox_min, ix->bbox_max, vp);
+  }
+  if (radius > 0.0f) {  // Some(radius); radius <= 0 finds nothing and is the kNN rule for everyone
+    if (shard_begin != 0 || shard_end < ix->n)
+      return tc_fail(ctx, TC_INVALID_DATA, "radius-mode normals are not sharded; pass the full range");
+    return tci_normals_radius_launch(ctx, ix, radius, k, consistent_orientation ? 1 : 0, vp, d_out_aos);
   }
   return tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, shard_begin, shard_end,
                             d_out_aos);

@@ -142,6 +142,10 @@ int tci_knn_launch(tc_context* ctx, const tc_index* index, const float4* d_queri
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out);
 int tci_normals_launch(tc_context* ctx, const tc_index* index, uint32_t k, int orient,
                        const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos);
+int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radius, uint32_t k,
+                              int orient, const float vp[3], float* d_out_aos);
+int tci_radius_search_launch(tc_context* ctx, const tc_index* index, const float q[3], float radius,
+                             uint32_t* d_idx, float* d_d2, uint32_t capacity, uint32_t* d_count);
 
 // ------------------------------------------------------------------------------------------
 // device helpers

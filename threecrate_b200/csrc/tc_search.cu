@@ -265,6 +265,48 @@ __device__ __forceinline__ void smallest_eigvec(const float cov[6] /*xx,xy,xz,yy
   n[2] = (float)ez;
 }
 
+// covariance (f32, already divided by n) -> unit eigenvector of the smallest eigenvalue,
+// renormalised, +z for a vanishing vector (normals.rs:181-202)
+__device__ __forceinline__ void normal_from_cov(const float c[6], float nrm[3]) {
+  smallest_eigvec(c, nrm);
+  const float mag =
+      xsqrt(xadd(xadd(xmul(nrm[0], nrm[0]), xmul(nrm[1], nrm[1])), xmul(nrm[2], nrm[2])));
+  if (mag > 1e-6f) {
+    nrm[0] = xdiv(nrm[0], mag);
+    nrm[1] = xdiv(nrm[1], mag);
+    nrm[2] = xdiv(nrm[2], mag);
+  } else {
+    nrm[0] = 0.0f;
+    nrm[1] = 0.0f;
+    nrm[2] = 1.0f;
+  }
+}
+// orientation (normals.rs:208-222: flip iff n . normalize(vp - p) < 0) and the NormalPoint3f row
+__device__ __forceinline__ void write_normal(float nrm[3], const float4 q, uint32_t qid, int orient,
+                                             float vpx, float vpy, float vpz,
+                                             float* __restrict__ out) {
+  if (orient) {
+    float tx = xsub(vpx, q.x), ty = xsub(vpy, q.y), tz = xsub(vpz, q.z);
+    const float mag = xsqrt(xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)));
+    tx = xdiv(tx, mag);
+    ty = xdiv(ty, mag);
+    tz = xdiv(tz, mag);
+    const float d = xadd(xadd(xmul(nrm[0], tx), xmul(nrm[1], ty)), xmul(nrm[2], tz));
+    if (d < 0.0f) {
+      nrm[0] = -nrm[0];
+      nrm[1] = -nrm[1];
+      nrm[2] = -nrm[2];
+    }
+  }
+  float* o = out + 6 * (uint64_t)qid;
+  o[0] = q.x;
+  o[1] = q.y;
+  o[2] = q.z;
+  o[3] = nrm[0];
+  o[4] = nrm[1];
+  o[5] = nrm[2];
+}
+
 // ------------------------------------------------------------------------------ normals kernel
 // Normal of one point from its ascending (d2, index) neighbour keys (normals.rs:306-354 body).
 template <class KS>
@@ -329,40 +371,9 @@ __device__ __forceinline__ void normals_emit(const KS& keys, const float4 q, uin
     acc(q.x, q.y, q.z);
 #pragma unroll
     for (int i = 0; i < 6; ++i) c[i] = xdiv(c[i], fn);
-    smallest_eigvec(c, nrm);
-    // renormalise, fall back to +z for a vanishing vector (normals.rs:197-202)
-    const float mag =
-        xsqrt(xadd(xadd(xmul(nrm[0], nrm[0]), xmul(nrm[1], nrm[1])), xmul(nrm[2], nrm[2])));
-    if (mag > 1e-6f) {
-      nrm[0] = xdiv(nrm[0], mag);
-      nrm[1] = xdiv(nrm[1], mag);
-      nrm[2] = xdiv(nrm[2], mag);
-    } else {
-      nrm[0] = 0.0f;
-      nrm[1] = 0.0f;
-      nrm[2] = 1.0f;
-    }
+    normal_from_cov(c, nrm);
   }
-  if (orient) {  // normals.rs:208-222: flip iff n . normalize(vp - p) < 0
-    float tx = xsub(vpx, q.x), ty = xsub(vpy, q.y), tz = xsub(vpz, q.z);
-    const float mag = xsqrt(xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)));
-    tx = xdiv(tx, mag);
-    ty = xdiv(ty, mag);
-    tz = xdiv(tz, mag);
-    const float d = xadd(xadd(xmul(nrm[0], tx), xmul(nrm[1], ty)), xmul(nrm[2], tz));
-    if (d < 0.0f) {
-      nrm[0] = -nrm[0];
-      nrm[1] = -nrm[1];
-      nrm[2] = -nrm[2];
-    }
-  }
-  float* o = out + 6 * (uint64_t)qid;
-  o[0] = q.x;
-  o[1] = q.y;
-  o[2] = q.z;
-  o[3] = nrm[0];
-  o[4] = nrm[1];
-  o[5] = nrm[2];
+  write_normal(nrm, q, qid, orient, vpx, vpy, vpz, out);
 }
 
 template <int K>
@@ -413,6 +424,105 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
   if (dbg) {
     dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
     dbg[2 * (size_t)qid + 1] = (uint32_t)n | ((uint32_t)level << 16);
+  }
+}
+
+// ------------------------------------------------------------------------------ radius mode
+// estimate_normals_with_config with radius = Some(r) (normals.rs:141-146, 315-340): neighbourhood
+// = every point with d2 <= r^2 except the query's own index, then the query itself.  Queries with
+// fewer than k such neighbours fall back to the kNN rule (appended to `fb_list`, finished by the
+// chain kernel).  The reference sums the neighbours in ascending-distance order in f32; here the
+// sums run in scan order but in f64 and are rounded to f32 once (the difference is the
+// reference's own f32 accumulation error).
+__global__ void __launch_bounds__(kBlock)
+k_normals_radius(LevelSet ls, int level, uint32_t n, float radius, uint32_t k, int orient, float vpx,
+                 float vpy, float vpz, float* __restrict__ out, uint32_t* __restrict__ fb_list,
+                 uint32_t* __restrict__ fb_count) {
+  const uint32_t qi = blockIdx.x * kBlock + threadIdx.x;
+  if (qi >= n) return;
+  const float4 q = __ldg(&ls.pts[0][qi]);
+  const uint32_t qid = __float_as_uint(q.w);
+  const GridParams& g = ls.g[level];
+  const float4* __restrict__ pts = ls.pts[level];
+  const float r2 = xmul(radius, radius);  // nearest_neighbor.rs:259
+  uint32_t cnt = 0;
+  double sx = 0, sy = 0, sz = 0;
+  box_visit(g, ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t j = lo; j < hi; ++j) {
+      const float4 c = __ldg(&pts[j]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, q.x, q.y, q.z);
+      if (d2 <= r2 && __float_as_uint(c.w) != qid) {
+        ++cnt;
+        sx += c.x;
+        sy += c.y;
+        sz += c.z;
+      }
+    }
+  });
+  if (cnt < k) {  // normals.rs:315-323
+    fb_list[atomicAdd(fb_count, 1u)] = qi;
+    return;
+  }
+  const uint32_t nn = cnt + 1;  // + the query itself (normals.rs:338-340)
+  const float fn = (float)nn;
+  const float cx = (float)((sx + q.x) / (double)nn), cy = (float)((sy + q.y) / (double)nn),
+              cz = (float)((sz + q.z) / (double)nn);
+  double m[6] = {0, 0, 0, 0, 0, 0};
+  auto acc = [&](float px, float py, float pz) {
+    const double dx = (double)xsub(px, cx), dy = (double)xsub(py, cy), dz = (double)xsub(pz, cz);
+    m[0] += dx * dx;
+    m[1] += dx * dy;
+    m[2] += dx * dz;
+    m[3] += dy * dy;
+    m[4] += dy * dz;
+    m[5] += dz * dz;
+  };
+  box_visit(g, ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t j = lo; j < hi; ++j) {
+      const float4 c = __ldg(&pts[j]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, q.x, q.y, q.z);
+      if (d2 <= r2 && __float_as_uint(c.w) != qid) acc(c.x, c.y, c.z);
+    }
+  });
+  acc(q.x, q.y, q.z);
+  float cov[6], nrm[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cov[i] = xdiv((float)m[i], fn);
+  normal_from_cov(cov, nrm);
+  write_normal(nrm, q, qid, orient, vpx, vpy, vpz, out);
+}
+
+// KdTree::find_radius_neighbors for ONE query (nearest_neighbor.rs:254-298): one block; warps take
+// rows of the box, lanes take candidates; hits are appended (unsorted) and ordered on the host.
+__global__ void __launch_bounds__(256)
+k_radius_search(LevelSet ls, int level, float qx, float qy, float qz, float radius,
+                uint32_t* __restrict__ idx_out, float* __restrict__ d2_out, uint32_t capacity,
+                uint32_t* __restrict__ n_found) {
+  const GridParams& g = ls.g[level];
+  const float4* __restrict__ pts = ls.pts[level];
+  const float r2 = xmul(radius, radius);
+  const float r = xsqrt(r2) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell) + 1e-30f;
+  float u;
+  const int xa = cell_coord(qx - r, g.ox, g.inv, g.nx, u), xb = cell_coord(qx + r, g.ox, g.inv, g.nx, u);
+  const int ya = cell_coord(qy - r, g.oy, g.inv, g.ny, u), yb = cell_coord(qy + r, g.oy, g.inv, g.ny, u);
+  const int za = cell_coord(qz - r, g.oz, g.inv, g.nz, u), zb = cell_coord(qz + r, g.oz, g.inv, g.nz, u);
+  const int ny = yb - ya + 1, nrows = ny * (zb - za + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < nrows; t += 8) {
+    const int z = za + t / ny, y = ya + t % ny;
+    const uint32_t row = cell_id(g, 0, y, z);
+    const uint32_t lo = __ldg(&ls.cs[level][row + xa]), hi = __ldg(&ls.cs[level][row + xb + 1]);
+    for (uint32_t j = lo + lane; j < hi; j += 32) {
+      const float4 c = __ldg(&pts[j]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+      if (d2 <= r2) {  // inclusive (nearest_neighbor.rs:270)
+        const uint32_t slot = atomicAdd(n_found, 1u);
+        if (slot < capacity) {
+          idx_out[slot] = __float_as_uint(c.w);
+          d2_out[slot] = d2;
+        }
+      }
+    }
   }
 }
 
@@ -540,5 +650,46 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
                         d_out_aos, d_fb + 1, d_fb, nullptr)));
   TC_LAUNCHED(ctx);
   tc_free(ctx, d_fb);
+  return TC_OK;
+}
+
+// Radius-mode normals for the whole cloud (no sharding of this mode yet).
+int tci_normals_radius_launch(tc_context* ctx, const tc_index* ix, float radius, uint32_t k,
+                              int orient, const float vp[3], float* d_out_aos) {
+  const uint32_t n = (uint32_t)ix->n;
+  if (n == 0) return TC_OK;
+  const int sz = pick_size(k + 1);
+  if (sz == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 63 for normals)");
+  const LevelSet ls = ix->level_set(g_tc_search_flags | 2);
+  // the level whose cell edge is closest to (and not far below) the radius keeps the box small
+  int level = 0;
+  for (int l = 0; l < ix->n_levels; ++l)
+    if (ix->lv[l].g.cell <= 2.0f * radius) level = l;
+  uint32_t* d_fb = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)n + 1));
+  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  const dim3 grid((n + kBlock - 1) / kBlock);
+  k_normals_radius<<<grid, kBlock, 0, ctx->stream>>>(ls, level, n, radius, k, orient, vp[0], vp[1],
+                                                     vp[2], d_out_aos, d_fb + 1, d_fb);
+  TC_LAUNCHED(ctx);
+  const dim3 fgrid(std::min<uint32_t>(grid.x, (uint32_t)ctx->sm_count * 4));
+  TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
+                        ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],
+                        d_out_aos, d_fb + 1, d_fb, nullptr)));
+  TC_LAUNCHED(ctx);
+  tc_free(ctx, d_fb);
+  return TC_OK;
+}
+
+int tci_radius_search_launch(tc_context* ctx, const tc_index* ix, const float q[3], float radius,
+                             uint32_t* d_idx, float* d_d2, uint32_t capacity, uint32_t* d_count) {
+  const LevelSet ls = ix->level_set(0);
+  int level = 0;
+  for (int l = 0; l < ix->n_levels; ++l)
+    if (ix->lv[l].g.cell <= 2.0f * radius) level = l;
+  k_radius_search<<<1, 256, 0, ctx->stream>>>(ls, level, q[0], q[1], q[2], radius, d_idx, d_d2,
+                                              capacity, d_count);
+  TC_LAUNCHED(ctx);
   return TC_OK;
 }
