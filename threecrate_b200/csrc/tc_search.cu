@@ -37,12 +37,6 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
   const float4* __restrict__ pts = ls.pts[level];
   const uint32_t* __restrict__ cell_start = ls.cs[level];
   const float tau = sel.kth();  // +inf when fewer than `need` points exist: everything is kept
-  // bit-equal real entries would collide in the rank placement -> exact chain kernel instead
-  bool tie = false;
-#pragma unroll
-  for (int i = 0; i + 1 < L; ++i)
-    if (sel.v[i] == sel.v[i + 1] && sel.v[i] >= 0.0f && sel.v[i] < INFINITY) tie = true;
-  if (tie) return -1;
   uint32_t n = 0;
   grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t j = lo; j < hi; ++j) {
@@ -54,7 +48,14 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
       }
     }
   });
-  if (n > need) return -1;  // tie straddling rank `need`: membership is decided by the index
+  if (n > (uint32_t)L) return -1;  // more ties than the table holds: exact chain kernel instead
+  // rank placement.  A member whose d2 is unique lands at #{v[i] < d2}.  Bit-equal d2 (inside
+  // the list, or at the K-th distance when more than `need` points are at or below it) are
+  // ordered by original index: such a member also counts the equal members with a smaller index.
+  bool any_tie = n > need;  // tie straddling rank `need`
+#pragma unroll
+  for (int i = 0; i + 1 < L; ++i)
+    if (sel.v[i] == sel.v[i + 1] && sel.v[i] >= 0.0f && sel.v[i] < INFINITY) any_tie = true;
 #pragma unroll 1
   for (uint32_t m = 0; m < n; ++m) {
     const uint32_t j = s_a[m][threadIdx.x];
@@ -63,8 +64,16 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
     int rank = -sel.pad;  // the sentinels are always below d2
 #pragma unroll
     for (int i = 0; i < L; ++i) rank += (sel.v[i] < d2) ? 1 : 0;
-    s_b[rank][threadIdx.x] = j;
+    if (any_tie) {  // rare: order bit-equal d2 by original index
+      const uint32_t id = __float_as_uint(c.w);
+      for (uint32_t o = 0; o < n; ++o) {
+        const float4 e = __ldg(&pts[s_a[o][threadIdx.x]]);
+        if (dist2_exact(e.x, e.y, e.z, qx, qy, qz) == d2 && __float_as_uint(e.w) < id) ++rank;
+      }
+    }
+    if (rank < (int)need) s_b[rank][threadIdx.x] = j;
   }
+  if (n > need) n = need;
   return (int)n;
 }
 
