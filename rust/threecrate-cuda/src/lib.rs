@@ -1,0 +1,165 @@
+//! threecrate-cuda: Rust host code over the `extern "C"` ABI of `include/threecrate_cuda.h`.
+//!
+//! UNCOMPILED in the build image (no cargo/rustc there) — this is the binding a maintainer adds;
+//! the same ABI is exercised from Python/ctypes by the test-suite of the CUDA repo.
+//!
+//! No wgpu, no multi-backend dispatch, no CPU fallback: with the `cuda` feature on, failures
+//! surface as `Error::Gpu`.
+use std::ffi::{c_char, c_int, c_void, CStr};
+use std::ptr;
+
+use nalgebra::{Isometry3, Quaternion, Translation3, UnitQuaternion};
+use threecrate_core::{Error, NormalPoint3f, Point3f, PointCloud, Result, Vector3f};
+
+#[repr(C)]
+pub struct TcContext { _p: [u8; 0] }
+#[repr(C)]
+pub struct TcCloud { _p: [u8; 0] }
+#[repr(C)]
+pub struct TcIndex { _p: [u8; 0] }
+
+#[repr(C)]
+#[derive(Default)]
+pub struct TcIcpResult {
+    pub transform: [f32; 7], // tx,ty,tz, qi,qj,qk,qw
+    pub mse: f32,
+    pub iterations: u32,
+    pub converged: i32,
+    pub n_correspondences: u64,
+}
+
+extern "C" {
+    fn tc_context_create(device: c_int, out: *mut *mut TcContext) -> c_int;
+    fn tc_context_destroy(ctx: *mut TcContext);
+    fn tc_last_error(ctx: *const TcContext) -> *const c_char;
+    fn tc_cloud_upload(ctx: *mut TcContext, xyz: *const f32, n: u64, out: *mut *mut TcCloud) -> c_int;
+    fn tc_cloud_free(c: *mut TcCloud);
+    fn tc_index_build(ctx: *mut TcContext, c: *const TcCloud, k_hint: u32, cell: f32,
+                      out: *mut *mut TcIndex) -> c_int;
+    fn tc_index_free(i: *mut TcIndex);
+    fn tc_knn(ctx: *mut TcContext, ix: *const TcIndex, queries: *const f32, nq: u64, k: u32,
+              exclude_self: c_int, idx: *mut u32, dist: *mut f32, count: *mut u32) -> c_int;
+    fn tc_estimate_normals(ctx: *mut TcContext, xyz: *const f32, n: u64, k: u32, radius: f32,
+                           consistent: c_int, viewpoint: *const f32, out: *mut f32) -> c_int;
+    fn tc_icp_point_to_plane(ctx: *mut TcContext, src: *const f32, ns: u64, tgt: *const f32, nt: u64,
+                             nrm: *const f32, nn: u64, init: *const f32, max_iters: u32,
+                             max_dist: f32, conv: f32, out: *mut TcIcpResult,
+                             pairs: *mut u64) -> c_int;
+}
+
+/// One context per thread (the C ABI serialises calls on a context's stream).
+pub struct Context(*mut TcContext);
+unsafe impl Send for Context {}
+
+thread_local! {
+    static CTX: Context = Context::new(0).expect("no CUDA device (the cuda feature has no CPU fallback)");
+}
+
+impl Context {
+    pub fn new(device: i32) -> Result<Self> {
+        let mut p = ptr::null_mut();
+        match unsafe { tc_context_create(device, &mut p) } {
+            0 => Ok(Self(p)),
+            _ => Err(Error::Gpu("no usable CUDA device".into())),
+        }
+    }
+    fn check(&self, st: c_int) -> Result<()> {
+        if st == 0 { return Ok(()); }
+        let msg = unsafe { CStr::from_ptr(tc_last_error(self.0)) }.to_string_lossy().into_owned();
+        Err(match st { 1 => Error::InvalidData(msg), 2 => Error::Algorithm(msg), _ => Error::Gpu(msg) })
+    }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { tc_context_destroy(self.0) } } }
+
+// `Point3<f32>` is a repr(C) newtype over [f32; 3]: `points.as_ptr() as *const f32` is the AoS the
+// ABI expects; `NormalPoint3f` is #[repr(C)] {position, normal} = 6 f32.
+
+/// Drop-in for `threecrate_algorithms::estimate_normals_with_config` (normals.rs:257).
+pub fn estimate_normals_with_config(points: &[Point3f], k: usize, radius: Option<f32>,
+                                    consistent_orientation: bool, viewpoint: Option<Point3f>)
+                                    -> Result<PointCloud<NormalPoint3f>> {
+    if points.is_empty() { return Ok(PointCloud::new()); }
+    let mut out: Vec<NormalPoint3f> = Vec::with_capacity(points.len());
+    CTX.with(|c| {
+        let vp = viewpoint.map(|p| [p.x, p.y, p.z]);
+        c.check(unsafe {
+            tc_estimate_normals(c.0, points.as_ptr() as *const f32, points.len() as u64, k as u32,
+                                radius.unwrap_or(-1.0), consistent_orientation as c_int,
+                                vp.as_ref().map_or(ptr::null(), |v| v.as_ptr()),
+                                out.as_mut_ptr() as *mut f32)
+        })
+    })?;
+    unsafe { out.set_len(points.len()) };
+    Ok(PointCloud::from_points(out))
+}
+
+/// Device-backed stand-in for `KdTree` (nearest_neighbor.rs:29): build once, query many.
+pub struct CudaKdTree { cloud: *mut TcCloud, index: *mut TcIndex, len: usize }
+
+impl CudaKdTree {
+    pub fn new(points: &[Point3f]) -> Result<Self> {
+        CTX.with(|c| {
+            let (mut cl, mut ix) = (ptr::null_mut(), ptr::null_mut());
+            c.check(unsafe { tc_cloud_upload(c.0, points.as_ptr() as *const f32, points.len() as u64, &mut cl) })?;
+            c.check(unsafe { tc_index_build(c.0, cl, 8, 0.0, &mut ix) })?;
+            Ok(Self { cloud: cl, index: ix, len: points.len() })
+        })
+    }
+    /// `NearestNeighborSearch::find_k_nearest` (traits.rs:6-12): (usize, f32) tuples are not
+    /// repr(C), so rows are repacked and u32 widened here.
+    pub fn find_k_nearest(&self, query: &Point3f, k: usize) -> Vec<(usize, f32)> {
+        if k == 0 || self.len == 0 { return Vec::new(); }
+        let (mut idx, mut dist, mut cnt) = (vec![0u32; k], vec![0f32; k], [0u32; 1]);
+        let q = [query.x, query.y, query.z];
+        CTX.with(|c| c.check(unsafe {
+            tc_knn(c.0, self.index, q.as_ptr(), 1, k as u32, 0, idx.as_mut_ptr(), dist.as_mut_ptr(), cnt.as_mut_ptr())
+        })).expect("tc_knn");
+        (0..cnt[0] as usize).map(|j| (idx[j] as usize, dist[j])).collect()
+    }
+    /// `PointCloudNeighbors::k_nearest_neighbors` (point_cloud_ops.rs:80-105).
+    pub fn k_nearest_neighbors(&self, k: usize) -> Vec<Vec<(usize, f32)>> {
+        if k == 0 || self.len == 0 { return Vec::new(); }
+        let n = self.len;
+        let (mut idx, mut dist, mut cnt) = (vec![0u32; n * k], vec![0f32; n * k], vec![0u32; n]);
+        CTX.with(|c| c.check(unsafe {
+            tc_knn(c.0, self.index, ptr::null(), n as u64, k as u32, 1, idx.as_mut_ptr(), dist.as_mut_ptr(), cnt.as_mut_ptr())
+        })).expect("tc_knn");
+        (0..n).map(|i| (0..cnt[i] as usize).map(|j| (idx[i * k + j] as usize, dist[i * k + j])).collect()).collect()
+    }
+}
+impl Drop for CudaKdTree { fn drop(&mut self) { unsafe { tc_index_free(self.index); tc_cloud_free(self.cloud) } } }
+
+/// Mirror of `threecrate_algorithms::ICPResult` fields (registration.rs:13-24).
+pub struct IcpOut {
+    pub transformation: Isometry3<f32>, pub mse: f32, pub iterations: usize, pub converged: bool,
+    pub correspondences: Vec<(usize, usize)>,
+}
+
+/// Drop-in for `icp_point_to_plane_detailed` (registration.rs:508).
+pub fn icp_point_to_plane_detailed(source: &[Point3f], target: &[Point3f], normals: &[Vector3f],
+                                   init: Isometry3<f32>, max_iters: usize, max_dist: Option<f32>,
+                                   conv: f32) -> Result<IcpOut> {
+    let q = init.rotation.quaternion().coords; // [i, j, k, w]
+    let t = init.translation.vector;
+    let init7 = [t.x, t.y, t.z, q[0], q[1], q[2], q[3]]; // never rely on Isometry3's layout
+    let mut res = TcIcpResult::default();
+    let mut pairs = vec![0u64; 2 * source.len().max(1)];
+    CTX.with(|c| c.check(unsafe {
+        tc_icp_point_to_plane(c.0, source.as_ptr() as *const f32, source.len() as u64,
+                              target.as_ptr() as *const f32, target.len() as u64,
+                              normals.as_ptr() as *const f32, normals.len() as u64, init7.as_ptr(),
+                              max_iters as u32, max_dist.unwrap_or(-1.0), conv, &mut res, pairs.as_mut_ptr())
+    }))?;
+    let r = res.transform;
+    let iso = Isometry3::from_parts(
+        Translation3::new(r[0], r[1], r[2]),
+        UnitQuaternion::new_unchecked(Quaternion::new(r[6], r[3], r[4], r[5])),
+    );
+    let m = res.n_correspondences as usize;
+    Ok(IcpOut { transformation: iso, mse: res.mse, iterations: res.iterations as usize,
+                converged: res.converged != 0,
+                correspondences: (0..m).map(|i| (pairs[2 * i] as usize, pairs[2 * i + 1] as usize)).collect() })
+}
+
+#[allow(dead_code)]
+fn _unused(_: *mut c_void) {}

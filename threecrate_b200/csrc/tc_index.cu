@@ -103,17 +103,20 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
 }
 
 // Counting-sort scatter: point i goes to cursor[cell(i)]++ as float4 (x, y, z, bits(i)).
-// `cursor` starts as a copy of cell_start.  The order INSIDE a cell is arrival order (not
+// The order INSIDE a cell is arrival order (not
 // deterministic) — nothing downstream depends on it: every selection is keyed by (d2, original
 // index) and multi-GPU shards own whole cells.
 __global__ void __launch_bounds__(kThreads) k_scatter_cells(const float* __restrict__ xyz,
                                                             const uint32_t* __restrict__ keys,
                                                             uint32_t n,
-                                                            uint32_t* __restrict__ cursor,
+                                                            const uint32_t* __restrict__ cell_start,
+                                                            uint32_t* __restrict__ counts,
                                                             float4* __restrict__ out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* p = xyz + 3 * (uint64_t)i;
-    const uint32_t pos = atomicAdd(&cursor[keys[i]], 1u);
+    const uint32_t c = keys[i];
+    // the histogram itself is the cursor: it counts down to zero while the cell fills up
+    const uint32_t pos = __ldg(&cell_start[c]) + atomicSub(&counts[c], 1u) - 1u;
     out[pos] = make_float4(p[0], p[1], p[2], __uint_as_float(i));
   }
 }
@@ -451,20 +454,15 @@ int level_finish(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, ui
   const uint64_t n = cloud->n;
   lv->g = g;
   lv->n_cells = (uint64_t)g.nx * g.ny * g.nz;
-  uint32_t* d_cursor = nullptr;
   int st = tc_alloc(ctx, &lv->d_cell_start, lv->n_cells + 1);
   if (st == TC_OK) st = tci_exclusive_scan_u32(ctx, d_counts, lv->d_cell_start, lv->n_cells);
-  if (st == TC_OK) st = tc_alloc(ctx, &d_cursor, lv->n_cells + 1);
   if (st == TC_OK) st = tc_alloc(ctx, &lv->d_pts, n);
   if (st == TC_OK) {
-    cudaMemcpyAsync(d_cursor, lv->d_cell_start, (lv->n_cells + 1) * sizeof(uint32_t),
-                    cudaMemcpyDeviceToDevice, ctx->stream);
     k_scatter_cells<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
-        cloud->d_xyz, d_keys, (uint32_t)n, d_cursor, lv->d_pts);
+        cloud->d_xyz, d_keys, (uint32_t)n, lv->d_cell_start, d_counts, lv->d_pts);
     ctx->launches++;
     if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "scatter launch failed");
   }
-  tc_free(ctx, d_cursor);
   return st;
 }
 
@@ -551,7 +549,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     if (st != TC_OK) break;
     if (!auto_cell || trial == max_trials - 1) break;
     const float pop = (float)n / (float)std::max(1u, stats[0]);
-    if (pop > target * 0.7f && pop < target * 1.4f) break;
+    if (pop > target * 0.5f && pop < target * 2.0f) break;
     // rescale assuming surface-like scaling (occupied cells ~ cell^-2); clamp the step
     float scale = std::sqrt(target / pop);
     scale = std::min(4.0f, std::max(0.25f, scale));
