@@ -161,6 +161,21 @@ int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud*
                                  const float init[7], uint32_t max_iters, float max_corr_dist,
                                  float conv_threshold, tc_icp_result* out, uint32_t* d_match_out);
 
+/* ---- point-to-point ICP (icp_detailed, registration.rs:258-370; the workload of the
+ *      reference's published benchmark, examples/threecrate_dataset_bench.rs:155-171) ----------
+ * Same conventions as the point-to-plane pair above.  < 3 valid pairs -> TC_ALGORITHM
+ * (registration.rs:311-315).  When not converged the reported mse is that of the last
+ * correspondences under the final transform (registration.rs:342-361).  The wrappers
+ * `icp_point_to_point` (conv_threshold <= 0 -> InvalidData, :665-669) and `icp` (errors -> init,
+ * :238-241) are host-side one-liners over this call. */
+int tc_icp_point_to_point(tc_context* ctx, const float* src_aos, uint64_t ns, const float* tgt_aos,
+                          uint64_t nt, const float init[7], uint32_t max_iters, float max_corr_dist,
+                          float conv_threshold, tc_icp_result* out, uint64_t* pairs_out);
+int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                                 const tc_index* tgt_index, const float init[7], uint32_t max_iters,
+                                 float max_corr_dist, float conv_threshold, tc_icp_result* out,
+                                 uint32_t* d_match_out);
+
 /* ---- multi-GPU (one process per GPU; NCCL bootstrap, id exchanged out of band) ------------- */
 #define TC_COMM_ID_BYTES 128
 int tc_comm_get_unique_id(tc_context* ctx, void* id_out /* TC_COMM_ID_BYTES */);

@@ -16,6 +16,7 @@ from .oracle import (  # noqa: F401
     build,
     estimate_normals,
     icp_point_to_plane,
+    icp_point_to_point,
     iso_apply,
     iso_mul,
     k_nearest_neighbors,

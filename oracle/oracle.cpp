@@ -1130,6 +1130,246 @@ int orc_icp_point_to_plane(const float* src, uint64_t ns, const float* tgt, uint
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Point-to-point ICP: icp_detailed (registration.rs:258-370), compute_transformation (:144-203),
+// compute_mse (:206-218).
+// Matrix3::svd and UnitQuaternion::from_matrix live in nalgebra [upstream, not under
+// /root/reference]: the SVD is restated with a one-sided Jacobi SVD in f32 (any backward-stable
+// SVD yields the same V U^T to ~1e-6), from_matrix with the standard matrix -> quaternion
+// conversion (the input is already a rotation, so nalgebra's iterative extraction is a no-op).
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+
+// one-sided Jacobi SVD of a 3x3: A = U diag(s) V^T  (f32)
+void svd3(const float a_in[3][3], float U[3][3], float S[3], float V[3][3]) {
+  float a[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      a[r][c] = a_in[r][c];
+      V[r][c] = r == c ? 1.0f : 0.0f;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    float off = 0.0f;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        float alpha = 0, beta = 0, gamma = 0;
+        for (int r = 0; r < 3; ++r) {
+          alpha += a[r][p] * a[r][p];
+          beta += a[r][q] * a[r][q];
+          gamma += a[r][p] * a[r][q];
+        }
+        off = std::max(off, std::fabs(gamma) / std::sqrt(std::max(alpha * beta, 1e-30f)));
+        if (gamma == 0.0f) continue;
+        const float zeta = (beta - alpha) / (2.0f * gamma);
+        const float t = std::copysign(1.0f, zeta) / (std::fabs(zeta) + std::sqrt(1.0f + zeta * zeta));
+        const float c = 1.0f / std::sqrt(1.0f + t * t), sn = c * t;
+        for (int r = 0; r < 3; ++r) {
+          const float x = a[r][p], y = a[r][q];
+          a[r][p] = c * x - sn * y;
+          a[r][q] = sn * x + c * y;
+          const float vx = V[r][p], vy = V[r][q];
+          V[r][p] = c * vx - sn * vy;
+          V[r][q] = sn * vx + c * vy;
+        }
+      }
+    if (off < 1e-7f) break;
+  }
+  for (int c = 0; c < 3; ++c) {
+    float n = 0;
+    for (int r = 0; r < 3; ++r) n += a[r][c] * a[r][c];
+    S[c] = std::sqrt(n);
+  }
+  // order descending so that a rank-deficient H puts its null direction last
+  int o[3] = {0, 1, 2};
+  std::sort(o, o + 3, [&](int x, int y) { return S[x] > S[y]; });
+  float a2[3][3], V2[3][3], S2[3];
+  for (int c = 0; c < 3; ++c) {
+    S2[c] = S[o[c]];
+    for (int r = 0; r < 3; ++r) {
+      a2[r][c] = a[r][o[c]];
+      V2[r][c] = V[r][o[c]];
+    }
+  }
+  for (int c = 0; c < 3; ++c) {
+    S[c] = S2[c];
+    for (int r = 0; r < 3; ++r) {
+      V[r][c] = V2[r][c];
+      U[r][c] = S2[c] > 0 ? a2[r][c] / S2[c] : 0.0f;
+    }
+  }
+  // complete U to an orthonormal basis when a singular value vanished
+  if (!(S[2] > 0)) {
+    const V3 u0{U[0][0], U[1][0], U[2][0]}, u1{U[0][1], U[1][1], U[2][1]};
+    const V3 u2 = cross(u0, u1);
+    U[0][2] = u2.x;
+    U[1][2] = u2.y;
+    U[2][2] = u2.z;
+  }
+}
+
+float det3(const float m[3][3]) {
+  return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) -
+         m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+         m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+
+Quat quat_from_rotation(const float R[3][3]) {  // Shepperd
+  Quat q;
+  const float tr = R[0][0] + R[1][1] + R[2][2];
+  if (tr > 0.0f) {
+    const float s = std::sqrt(tr + 1.0f) * 2.0f;
+    q.w = 0.25f * s;
+    q.i = (R[2][1] - R[1][2]) / s;
+    q.j = (R[0][2] - R[2][0]) / s;
+    q.k = (R[1][0] - R[0][1]) / s;
+  } else if (R[0][0] > R[1][1] && R[0][0] > R[2][2]) {
+    const float s = std::sqrt(1.0f + R[0][0] - R[1][1] - R[2][2]) * 2.0f;
+    q.w = (R[2][1] - R[1][2]) / s;
+    q.i = 0.25f * s;
+    q.j = (R[0][1] + R[1][0]) / s;
+    q.k = (R[0][2] + R[2][0]) / s;
+  } else if (R[1][1] > R[2][2]) {
+    const float s = std::sqrt(1.0f + R[1][1] - R[0][0] - R[2][2]) * 2.0f;
+    q.w = (R[0][2] - R[2][0]) / s;
+    q.i = (R[0][1] + R[1][0]) / s;
+    q.j = 0.25f * s;
+    q.k = (R[1][2] + R[2][1]) / s;
+  } else {
+    const float s = std::sqrt(1.0f + R[2][2] - R[0][0] - R[1][1]) * 2.0f;
+    q.w = (R[1][0] - R[0][1]) / s;
+    q.i = (R[0][2] + R[2][0]) / s;
+    q.j = (R[1][2] + R[2][1]) / s;
+    q.k = 0.25f * s;
+  }
+  return q;
+}
+
+// compute_transformation (registration.rs:144-203)
+Iso kabsch(const std::vector<V3>& src, const std::vector<V3>& tgt) {
+  const float n = (float)src.size();
+  V3 cs{0, 0, 0}, ct{0, 0, 0};
+  for (const V3& p : src) cs = V3{cs.x + p.x, cs.y + p.y, cs.z + p.z};
+  for (const V3& p : tgt) ct = V3{ct.x + p.x, ct.y + p.y, ct.z + p.z};
+  cs = V3{cs.x / n, cs.y / n, cs.z / n};
+  ct = V3{ct.x / n, ct.y / n, ct.z / n};
+  float H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (size_t i = 0; i < src.size(); ++i) {
+    const float p[3] = {src[i].x - cs.x, src[i].y - cs.y, src[i].z - cs.z};
+    const float q[3] = {tgt[i].x - ct.x, tgt[i].y - ct.y, tgt[i].z - ct.z};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) H[r][c] += p[r] * q[c];
+  }
+  float U[3][3], S[3], V[3][3];
+  svd3(H, U, S, V);
+  auto vut = [&](float R[3][3]) {  // R = V U^T
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        R[r][c] = 0;
+        for (int k = 0; k < 3; ++k) R[r][c] += V[r][k] * U[c][k];
+      }
+  };
+  float R[3][3];
+  vut(R);
+  if (det3(R) < 0.0f) {  // flip the last row of V^T == last column of V (:187-191)
+    for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
+    vut(R);
+  }
+  const Quat q = quat_from_rotation(R);
+  const V3 rc = quat_rotate(q, cs);
+  return Iso{q, V3{ct.x - rc.x, ct.y - rc.y, ct.z - rc.z}};
+}
+
+float mse_pairs(const std::vector<V3>& a, const std::vector<V3>& b) {  // :206-218
+  if (a.empty()) return 0.0f;
+  float sum = 0.0f;
+  for (size_t i = 0; i < a.size(); ++i) {
+    const float dx = a[i].x - b[i].x, dy = a[i].y - b[i].y, dz = a[i].z - b[i].z;
+    sum += dx * dx + dy * dy + dz * dz;
+  }
+  return sum / (float)a.size();
+}
+
+}  // namespace
+extern "C" {
+
+// icp_detailed (registration.rs:258-370).  Returns 0 OK, 1 InvalidData, 2 Algorithm.
+int orc_icp_point_to_point(const float* src, uint64_t ns, const float* tgt, uint64_t nt,
+                           const float* init7, uint64_t max_iters, float max_dist, float conv,
+                           orc_icp_result* res, uint64_t* pairs_out, int threads) {
+  if (ns == 0 || nt == 0) return 1;  // :266-270
+  if (max_iters == 0) return 1;      // :272-276
+  Iso T{Quat{init7[3], init7[4], init7[5], init7[6]}, V3{init7[0], init7[1], init7[2]}};
+  float previous_mse = INFINITY;
+  std::vector<std::pair<uint64_t, uint64_t>> final_corr, corr_pairs;
+  KdTree* tree = kd_new(tgt, nt);
+  std::vector<V3> ts(ns), vs, vt;
+  std::vector<int64_t> corr_idx(ns);
+  const int nth = threads > 0 ? threads : orc_max_threads();
+  auto finish = [&](float mse, uint64_t iters, int converged,
+                    const std::vector<std::pair<uint64_t, uint64_t>>& pairs) {
+    res->t[0] = T.t.x; res->t[1] = T.t.y; res->t[2] = T.t.z;
+    res->q[0] = T.q.i; res->q[1] = T.q.j; res->q[2] = T.q.k; res->q[3] = T.q.w;
+    res->mse = mse;
+    res->iterations = iters;
+    res->converged = converged;
+    res->n_corr = pairs.size();
+    if (pairs_out)
+      for (size_t i = 0; i < pairs.size(); ++i) {
+        pairs_out[2 * i] = pairs[i].first;
+        pairs_out[2 * i + 1] = pairs[i].second;
+      }
+  };
+  for (uint64_t iteration = 0; iteration < max_iters; ++iteration) {
+    for (uint64_t i = 0; i < ns; ++i)
+      ts[i] = iso_apply(T, V3{src[3 * i], src[3 * i + 1], src[3 * i + 2]});
+#pragma omp parallel num_threads(nth)
+    {
+      std::vector<Neighbor> out;
+      std::vector<uint32_t> stack;
+#pragma omp for schedule(dynamic, 256)
+      for (int64_t i = 0; i < (int64_t)ns; ++i) {
+        kd_find_k_nearest(*tree, P3{ts[i].x, ts[i].y, ts[i].z}, 1, out, stack);
+        if (out.empty()) { corr_idx[i] = -1; continue; }
+        const float distance = std::sqrt(out[0].distance);
+        corr_idx[i] = (max_dist >= 0.0f && distance > max_dist) ? -1 : (int64_t)out[0].index;
+      }
+    }
+    vs.clear(); vt.clear(); corr_pairs.clear();
+    for (uint64_t i = 0; i < ns; ++i) {
+      if (corr_idx[i] < 0) continue;
+      const uint64_t j = (uint64_t)corr_idx[i];
+      vs.push_back(ts[i]);
+      vt.push_back(V3{tgt[3 * j], tgt[3 * j + 1], tgt[3 * j + 2]});
+      corr_pairs.emplace_back(i, j);
+    }
+    if (vs.size() < 3) { delete tree; return 2; }  // :311-315
+    const Iso delta = kabsch(vs, vt);
+    T = iso_mul(delta, T);
+    const float current_mse = mse_pairs(vs, vt);
+    if (std::fabs(previous_mse - current_mse) < conv) {  // :327-336
+      finish(current_mse, iteration + 1, 1, corr_pairs);
+      delete tree;
+      return 0;
+    }
+    previous_mse = current_mse;
+    final_corr = corr_pairs;
+  }
+  delete tree;
+  // :342-361 — mse of the LAST correspondences under the FINAL transform
+  float final_mse = previous_mse;
+  if (!final_corr.empty()) {
+    vs.clear(); vt.clear();
+    for (auto& pr : final_corr) {
+      vs.push_back(iso_apply(T, V3{src[3 * pr.first], src[3 * pr.first + 1], src[3 * pr.first + 2]}));
+      vt.push_back(V3{tgt[3 * pr.second], tgt[3 * pr.second + 1], tgt[3 * pr.second + 2]});
+    }
+    final_mse = mse_pairs(vs, vt);
+  }
+  finish(final_mse, max_iters, 0, final_corr);
+  return 0;
+}
+
 // Helpers exposed for unit tests of the nalgebra restatements.
 void orc_iso_apply(const float* iso7, const float* p3, float* out3) {
   const Iso T{Quat{iso7[3], iso7[4], iso7[5], iso7[6]}, V3{iso7[0], iso7[1], iso7[2]}};

@@ -65,6 +65,9 @@ def _load():
     lib.orc_icp_point_to_plane.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_uint64,
                                            _f32p, C.c_uint64, C.c_float, C.c_float,
                                            C.POINTER(_IcpRes), _u64p, C.c_int]
+    lib.orc_icp_point_to_point.restype = C.c_int
+    lib.orc_icp_point_to_point.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_uint64,
+                                           C.c_float, C.c_float, C.POINTER(_IcpRes), _u64p, C.c_int]
     lib.orc_iso_apply.argtypes = [_f32p, _f32p, _f32p]
     lib.orc_iso_mul.argtypes = [_f32p, _f32p, _f32p]
     lib.orc_solve6.restype = C.c_int
@@ -233,6 +236,29 @@ def icp_point_to_plane(source, target, target_normals, init=None, max_iters: int
         raise InvalidData("invalid ICP arguments")
     if st == 2:
         raise AlgorithmError("ICP numerical failure")
+    return IcpResult(np.array(res.t[:], np.float32), np.array(res.q[:], np.float32),
+                     float(res.mse), int(res.iterations), bool(res.converged),
+                     pairs[: res.n_corr].copy())
+
+
+def icp_point_to_point(source, target, init=None, max_iters: int = 50, conv: float = 1e-6,
+                       max_dist=None, threads: int = 0, validate_conv: bool = True) -> IcpResult:
+    """icp_point_to_point (registration.rs:644-680) -> icp_detailed (:258-370)."""
+    src = _f32(source, (-1, 3))
+    tgt = _f32(target, (-1, 3))
+    if validate_conv and src.shape[0] and tgt.shape[0] and max_iters and conv <= 0.0:
+        raise InvalidData("Convergence threshold must be positive")  # :665-669
+    init7 = _f32([0, 0, 0, 0, 0, 0, 1] if init is None else init, (7,))
+    res = _IcpRes()
+    pairs = np.zeros((max(src.shape[0], 1), 2), np.uint64)
+    st = _load().orc_icp_point_to_point(
+        _p(src, _f32p), src.shape[0], _p(tgt, _f32p), tgt.shape[0], _p(init7, _f32p),
+        int(max_iters), -1.0 if max_dist is None else float(max_dist), float(conv),
+        C.byref(res), _p(pairs, _u64p), threads)
+    if st == 1:
+        raise InvalidData("invalid ICP arguments")
+    if st == 2:
+        raise AlgorithmError("Insufficient correspondences found")
     return IcpResult(np.array(res.t[:], np.float32), np.array(res.q[:], np.float32),
                      float(res.mse), int(res.iterations), bool(res.converged),
                      pairs[: res.n_corr].copy())

@@ -27,7 +27,10 @@ from .api import (  # noqa: F401
     estimate_normals,
     estimate_normals_radius,
     estimate_normals_with_config,
+    icp,
+    icp_detailed,
     icp_point_to_plane,
+    icp_point_to_point,
     icp_point_to_plane_detailed,
     icp_point_to_plane_device,
     k_nearest_neighbors,

@@ -79,6 +79,10 @@ SYMBOLS = {
                                         C.c_uint32, C.c_float, C.c_float, C.POINTER(IcpResultC), _vp]),
     "tc_icp_point_to_plane_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32p, C.c_uint32, C.c_float,
                                                C.c_float, C.POINTER(IcpResultC), _vp]),
+    "tc_icp_point_to_point": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _f32p, C.c_uint32,
+                                        C.c_float, C.c_float, C.POINTER(IcpResultC), _vp]),
+    "tc_icp_point_to_point_device": (C.c_int, [_vp, _vp, _vp, _vp, _f32p, C.c_uint32, C.c_float,
+                                               C.c_float, C.POINTER(IcpResultC), _vp]),
     "tc_comm_get_unique_id": (C.c_int, [_vp, _vp]),
     "tc_comm_init_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "tc_comm_destroy": (None, [_vp]),

@@ -389,6 +389,52 @@ def icp_point_to_plane(source, target, target_normals, init=IDENTITY, max_iters:
                                        ctx)
 
 
+def icp_detailed(source, target, init=IDENTITY, max_iters: int = 50,
+                 max_correspondence_distance: Optional[float] = None,
+                 convergence_threshold: float = 1e-6, ctx: Optional[Context] = None,
+                 want_correspondences: bool = True) -> ICPResult:
+    """Point-to-point ICP, registration.rs:258-370."""
+    src, tgt = _pts(source, "source"), _pts(target, "target")
+    init7 = np.ascontiguousarray(init, np.float32).reshape(7)
+    ctx = ctx or default_context()
+    res = _lib.IcpResultC()
+    pairs = np.zeros((max(src.shape[0], 1), 2), np.uint64) if want_correspondences else None
+    ctx.check(ctx.lib.tc_icp_point_to_point(
+        ctx.h, _vp(src.ctypes.data), src.shape[0], _vp(tgt.ctypes.data), tgt.shape[0],
+        init7.ctypes.data_as(C.POINTER(C.c_float)), int(max_iters),
+        -1.0 if max_correspondence_distance is None else float(max_correspondence_distance),
+        float(convergence_threshold), C.byref(res),
+        None if pairs is None else _vp(pairs.ctypes.data)))
+    corr = pairs[: res.n_correspondences].copy() if pairs is not None else np.empty((0, 2), np.uint64)
+    return ICPResult(np.array(res.transform[:], np.float32), float(res.mse), int(res.iterations),
+                     bool(res.converged), corr)
+
+
+def icp_point_to_point(source, target, init=IDENTITY, max_iterations: int = 50,
+                       convergence_threshold: float = 1e-6,
+                       max_correspondence_distance: Optional[float] = None,
+                       ctx: Optional[Context] = None) -> ICPResult:
+    """registration.rs:644-680 (argument order of the reference)."""
+    src, tgt = _pts(source, "source"), _pts(target, "target")
+    if src.shape[0] == 0 or tgt.shape[0] == 0:
+        raise InvalidData("Source or target point cloud is empty")
+    if max_iterations == 0:
+        raise InvalidData("Max iterations must be positive")
+    if convergence_threshold <= 0.0:
+        raise InvalidData("Convergence threshold must be positive")
+    return icp_detailed(src, tgt, init, max_iterations, max_correspondence_distance,
+                        convergence_threshold, ctx)
+
+
+def icp(source, target, init=IDENTITY, max_iters: int = 50, ctx: Optional[Context] = None) -> np.ndarray:
+    """registration.rs:232-242: the final transformation, or `init` on ANY error."""
+    try:
+        return icp_detailed(source, target, init, max_iters, None, 1e-6, ctx,
+                            want_correspondences=False).transformation
+    except ThreecrateError:
+        return np.ascontiguousarray(init, np.float32).reshape(7)
+
+
 # --------------------------------------------------------------------------------------------
 # multi-GPU (one process per GPU)
 # --------------------------------------------------------------------------------------------

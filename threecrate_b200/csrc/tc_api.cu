@@ -502,3 +502,48 @@ extern "C" int tc_icp_point_to_plane(tc_context* ctx, const float* src_aos, uint
   tc_cloud_free(src);
   return st;
 }
+
+extern "C" int tc_icp_point_to_point(tc_context* ctx, const float* src_aos, uint64_t ns,
+                                     const float* tgt_aos, uint64_t nt, const float init[7],
+                                     uint32_t max_iters, float max_corr_dist, float conv_threshold,
+                                     tc_icp_result* out, uint64_t* pairs_out) {
+  TC_ENTER(ctx);
+  // validation order of registration.rs:266-276
+  if (ns == 0 || nt == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
+  if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
+  if (!src_aos || !tgt_aos || !init || !out) return TC_INVALID_DATA;
+  tc_cloud *src = nullptr, *tgt = nullptr;
+  tc_index* ix = nullptr;
+  uint32_t* d_match = nullptr;
+  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
+  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
+  if (st == TC_OK) st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);  // KdTree::new(target), :281
+  if (st == TC_OK && pairs_out) st = tc_alloc(ctx, &d_match, ns);
+  if (st == TC_OK)
+    st = tc_icp_point_to_point_device(ctx, nullptr, src, ix, init, max_iters, max_corr_dist,
+                                      conv_threshold, out, d_match);
+  if (st == TC_OK && pairs_out) {
+    std::vector<uint32_t> match(ns);
+    cudaError_t e = cudaMemcpyAsync(match.data(), d_match, ns * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      st = tc_fail(ctx, TC_GPU, std::string("ICP pairs: ") + cudaGetErrorString(e));
+    } else {
+      uint64_t c = 0;
+      for (uint64_t i = 0; i < ns; ++i)
+        if (match[i] != TC_NO_INDEX) {
+          pairs_out[2 * c] = i;
+          pairs_out[2 * c + 1] = match[i];
+          ++c;
+        }
+      out->n_correspondences = c;
+    }
+  }
+  tc_free(ctx, d_match);
+  tc_index_free(ix);
+  tc_cloud_free(tgt);
+  tc_cloud_free(src);
+  return st;
+}

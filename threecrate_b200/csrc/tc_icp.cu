@@ -23,7 +23,9 @@ namespace {
 using namespace tcs;
 
 constexpr int kIcpBlock = 256;
-constexpr int kNumSums = 29;  // 21 + 6 + 1 + 1
+constexpr int kNumSums = 29;   // point-to-plane: 21 AtA + 6 Atb + sum b^2 + n_valid
+constexpr int kNumSumsP2P = 17; // point-to-point: sum s (3) + sum t (3) + sum s t^T (9) + sum |s-t|^2 + n
+constexpr int kPlane = 0, kPoint = 1;
 
 struct IcpState {
   float T[7];          // tx,ty,tz, qi,qj,qk,qw
@@ -90,6 +92,7 @@ k_pad_normals(const float* __restrict__ nrm, uint32_t n, float4* __restrict__ ou
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kIcpBlock)
 k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
                  const float4* __restrict__ src, uint32_t ns,
@@ -103,9 +106,10 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   // Per-thread partials in f32: the products a_i a_j are f32 in the reference too
   // (registration.rs:426-427) and a thread only sums a handful of points; everything across
   // threads (warp, block, grid) is reduced in f64.
-  float acc[kNumSums];
+  constexpr int NS = MODE == kPlane ? kNumSums : kNumSumsP2P;
+  float acc[NS];
 #pragma unroll
-  for (int i = 0; i < kNumSums; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < NS; ++i) acc[i] = 0.0f;
 
   for (uint32_t i = blockIdx.x * kIcpBlock + threadIdx.x; i < ns; i += gridDim.x * kIcpBlock) {
     const float4 s4 = __ldg(&src[i]);
@@ -142,38 +146,53 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
     if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
     if (valid) {
       const float4 d4 = __ldg(&ls.pts[level][best.pos]);
-      const float4 n4 = __ldg(&tgt_nrm[__float_as_uint(d4.w)]);
-      const V3 n{n4.x, n4.y, n4.z};
-      const V3 c = xcross(s, n);  // registration.rs:418
-      const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
-      const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
-      const float a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
+      if (MODE == kPlane) {
+        const float4 n4 = __ldg(&tgt_nrm[__float_as_uint(d4.w)]);
+        const V3 n{n4.x, n4.y, n4.z};
+        const V3 c = xcross(s, n);  // registration.rs:418
+        const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
+        const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
+        const float a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+        for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int cc = r; cc < 6; ++cc)
-          acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += xmul(a[r], a[cc]);
+          for (int cc = r; cc < 6; ++cc)
+            acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += xmul(a[r], a[cc]);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += xmul(a[r], b);
-      acc[27] += xmul(b, b);
-      acc[28] += 1.0f;
+        for (int r = 0; r < 6; ++r) acc[21 + r] += xmul(a[r], b);
+        acc[27] += xmul(b, b);
+        acc[28] += 1.0f;
+      } else {
+        // raw moments for Kabsch (registration.rs:157-172) and the mse (:206-218)
+        const float sv[3] = {s.x, s.y, s.z}, tv[3] = {d4.x, d4.y, d4.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          acc[r] += sv[r];
+          acc[3 + r] += tv[r];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) acc[6 + 3 * r + cc] += xmul(sv[r], tv[cc]);
+        }
+        const float dx = xsub(s.x, d4.x), dy = xsub(s.y, d4.y), dz = xsub(s.z, d4.z);
+        acc[15] += xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+        acc[16] += 1.0f;
+      }
     }
   }
   // warp-shuffle tree, then one row per warp in shared memory
-  __shared__ double sm[kIcpBlock / 32][kNumSums];
+  __shared__ double sm[kIcpBlock / 32][NS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < kNumSums; ++i) {
+  for (int i = 0; i < NS; ++i) {
     double v = (double)acc[i];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sm[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < kNumSums) {
+  if (threadIdx.x < NS) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kIcpBlock / 32; ++w) v += sm[w][threadIdx.x];
-    partials[(uint64_t)blockIdx.x * kNumSums + threadIdx.x] = v;
+    partials[(uint64_t)blockIdx.x * NS + threadIdx.x] = v;
   }
   __threadfence();
   __shared__ bool last;
@@ -182,10 +201,10 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   __syncthreads();
   if (last) {
     __threadfence();
-    if (threadIdx.x < kNumSums) {
+    if (threadIdx.x < NS) {
       double v = 0.0;
       for (uint32_t b = 0; b < gridDim.x; ++b)
-        v += __ldcg(&partials[(uint64_t)b * kNumSums + threadIdx.x]);
+        v += __ldcg(&partials[(uint64_t)b * NS + threadIdx.x]);
       sums[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) st->ticket = 0;
@@ -270,6 +289,9 @@ __device__ int solve6(const double* s /*21 upper-tri row-major*/, const double* 
   return 0;
 }
 
+__device__ void icp_apply_delta(IcpState* st, const float dq[4], const float dt[3], float mse,
+                                float conv);
+
 __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ sums, float conv) {
   if (threadIdx.x != 0 || st->done) return;
   const double n_valid = sums[28];
@@ -298,7 +320,17 @@ __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict_
   quat_mul(qz, qy, qzy);
   quat_mul(qzy, qx, dq);
   const float dt[3] = {(float)x[3], (float)x[4], (float)x[5]};
-  // T <- delta * T = (dq * q, dt + dq . t)   (registration.rs:576)  [nalgebra Isometry3 product]
+  // mean b^2 over valid pairs, residuals taken BEFORE delta (registration.rs:453-471, 578);
+  // T <- delta * T = (dq * q, dt + dq . t) (registration.rs:576) [nalgebra Isometry3 product]
+  const float mse = (float)(sums[27] / n_valid);
+  icp_apply_delta(st, dq, dt, mse, conv);
+}
+
+
+// Shared tail of both solve kernels: T <- delta o T, mse, convergence (registration.rs:321-338,
+// 576-589).  dq = [i,j,k,w].
+__device__ void icp_apply_delta(IcpState* st, const float dq[4], const float dt[3], float mse,
+                                float conv) {
   float q_old[4] = {st->T[3], st->T[4], st->T[5], st->T[6]};
   const V3 sh = quat_rotate(dq, V3{st->T[0], st->T[1], st->T[2]});
   float qn[4];
@@ -310,11 +342,9 @@ __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict_
   st->T[4] = qn[1];
   st->T[5] = qn[2];
   st->T[6] = qn[3];
-  // mean b^2 over valid pairs, residuals taken BEFORE delta (registration.rs:453-471, 578)
-  const float mse = (float)(sums[27] / n_valid);
   st->iterations += 1;
   st->mse = mse;
-  if (fabsf(st->prev_mse - mse) < conv) {  // registration.rs:579-589
+  if (fabsf(st->prev_mse - mse) < conv) {
     st->converged = 1;
     st->done = 1;
     return;
@@ -322,23 +352,150 @@ __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict_
   st->prev_mse = mse;
 }
 
+// Point-to-point step (compute_transformation, registration.rs:144-203): the rotation maximising
+// trace(R H) with det R = +1.  The reference takes V U^T from an SVD of H and flips the last
+// singular vector on a reflection; the same proper rotation is the dominant eigenvector of Horn's
+// symmetric 4x4 matrix built from H, found here by cyclic Jacobi in f64.
+__global__ void k_icp_solve_p2p(IcpState* __restrict__ st, const double* __restrict__ sums,
+                                float conv) {
+  if (threadIdx.x != 0 || st->done) return;
+  const double n = sums[16];
+  st->n_valid = n;
+  if (n < 3.0) {  // registration.rs:311-315
+    st->status = 2;
+    st->done = 1;
+    return;
+  }
+  double cs[3], ct[3], H[3][3];
+  for (int a = 0; a < 3; ++a) {
+    cs[a] = sums[a] / n;
+    ct[a] = sums[3 + a] / n;
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) H[r][c] = sums[6 + 3 * r + c] - n * cs[r] * ct[c];
+  double N[4][4];
+  N[0][0] = H[0][0] + H[1][1] + H[2][2];
+  N[0][1] = H[1][2] - H[2][1];
+  N[0][2] = H[2][0] - H[0][2];
+  N[0][3] = H[0][1] - H[1][0];
+  N[1][1] = H[0][0] - H[1][1] - H[2][2];
+  N[1][2] = H[0][1] + H[1][0];
+  N[1][3] = H[2][0] + H[0][2];
+  N[2][2] = -H[0][0] + H[1][1] - H[2][2];
+  N[2][3] = H[1][2] + H[2][1];
+  N[3][3] = -H[0][0] - H[1][1] + H[2][2];
+  for (int r = 1; r < 4; ++r)
+    for (int c = 0; c < r; ++c) N[r][c] = N[c][r];
+  double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) (r == c ? dg : off) += N[r][c] * N[r][c];
+    if (off <= 1e-30 * dg || off == 0.0) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        if (N[p][q] == 0.0) continue;
+        const double theta = (N[q][q] - N[p][p]) / (2.0 * N[p][q]);
+        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 4; ++k) {
+          const double a = N[k][p], b = N[k][q];
+          N[k][p] = c * a - s * b;
+          N[k][q] = s * a + c * b;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double a = N[p][k], b = N[q][k];
+          N[p][k] = c * a - s * b;
+          N[q][k] = s * a + c * b;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double a = V[k][p], b = V[k][q];
+          V[k][p] = c * a - s * b;
+          V[k][q] = s * a + c * b;
+        }
+      }
+  }
+  int m = 0;
+  for (int i = 1; i < 4; ++i)
+    if (N[i][i] > N[m][m]) m = i;
+  double qw = V[0][m], qx = V[1][m], qy = V[2][m], qz = V[3][m];
+  const double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+  if (!(qn > 0.0) || !isfinite(qn)) {
+    st->status = 3;
+    st->done = 1;
+    return;
+  }
+  const double sg = qw < 0.0 ? -1.0 / qn : 1.0 / qn;  // w >= 0, like a matrix -> quaternion conversion
+  qw *= sg;
+  qx *= sg;
+  qy *= sg;
+  qz *= sg;
+  // translation = target_centroid - rotation * source_centroid (registration.rs:197)
+  const double R[3][3] = {
+      {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)},
+      {2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)},
+      {2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)}};
+  float dt[3];
+  for (int r = 0; r < 3; ++r)
+    dt[r] = (float)(ct[r] - (R[r][0] * cs[0] + R[r][1] * cs[1] + R[r][2] * cs[2]));
+  const float dq[4] = {(float)qx, (float)qy, (float)qz, (float)qw};
+  const float mse = (float)(sums[15] / n);  // pre-delta residuals (registration.rs:324)
+  icp_apply_delta(st, dq, dt, mse, conv);
+}
+
+// Not converged: the reference reports the mse of the LAST correspondences under the FINAL
+// transform (registration.rs:342-361).  prev[] holds the last matches (level << 30 | position).
+__global__ void __launch_bounds__(kIcpBlock)
+k_icp_p2p_final_mse(LevelSet ls, const float4* __restrict__ src, uint32_t ns,
+                    const uint32_t* __restrict__ prev, const IcpState* __restrict__ st,
+                    double* __restrict__ out2 /* [sum, count], zeroed */) {
+  float T[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T[i] = st->T[i];
+  double sum = 0.0, cnt = 0.0;
+  for (uint32_t i = blockIdx.x * kIcpBlock + threadIdx.x; i < ns; i += gridDim.x * kIcpBlock) {
+    const uint32_t m = prev[i];
+    if (m == 0xFFFFFFFFu) continue;
+    const float4 s4 = __ldg(&src[i]);
+    V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
+    s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
+    const float4 t4 = __ldg(&ls.pts[m >> 30][m & 0x3FFFFFFFu]);
+    const float dx = xsub(s.x, t4.x), dy = xsub(s.y, t4.y), dz = xsub(s.z, t4.z);
+    sum += (double)xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+    cnt += 1.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+    atomicAdd(&out2[0], sum);
+    atomicAdd(&out2[1], cnt);
+  }
+}
+
 }  // namespace
 
-extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
-                                            const tc_index* tgt, const float* d_tgt_normals_aos,
-                                            const float init[7], uint32_t max_iters,
-                                            float max_corr_dist, float conv_threshold,
-                                            tc_icp_result* out, uint32_t* d_match_out) {
+namespace {
+
+// Shared driver of the device-resident ICP loops (mode: kPlane / kPoint).
+int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                    const tc_index* tgt, const float* d_tgt_normals_aos, const float init[7],
+                    uint32_t max_iters, float max_corr_dist, float conv_threshold,
+                    tc_icp_result* out, uint32_t* d_match_out) {
   if (!ctx || !src || !tgt || !out || !init) return TC_INVALID_DATA;
-  // validation order of registration.rs:517-531 (normals length is checked by the host wrapper)
+  // validation order of registration.rs:266-276 / 517-531 (normals length: host wrapper)
   if ((src->n == 0 && !comm) || tgt->n == 0)
     return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
-  if (!d_tgt_normals_aos)
+  if (mode == kPlane && !d_tgt_normals_aos)
     return tc_fail(ctx, TC_INVALID_DATA,
                    "target_normals length must equal the number of target points");
   if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
   const uint32_t ns = (uint32_t)src->n;
   const uint32_t nt = (uint32_t)tgt->n;
+  if (mode == kPoint && nt >= (1u << 30))
+    return tc_fail(ctx, TC_INVALID_DATA, "point-to-point ICP supports targets below 2^30 points");
+  const int n_sums = mode == kPlane ? kNumSums : kNumSumsP2P;
 
   // sort the source spatially (own bbox, target-sized cells) so warps walk coherent target cells
   float4* d_src = nullptr;
@@ -366,39 +523,63 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
   float4* d_nrm = nullptr;
   uint32_t* d_prev = nullptr;
   IcpState* d_state = nullptr;
-  double *d_partials = nullptr, *d_sums = nullptr;
-  int st = tc_alloc(ctx, &d_nrm, nt);
+  double *d_partials = nullptr, *d_sums = nullptr, *d_final = nullptr;
+  int st = TC_OK;
+  if (mode == kPlane) st = tc_alloc(ctx, &d_nrm, nt);
   if (st == TC_OK) st = tc_alloc(ctx, &d_state, 1);
   if (st == TC_OK && nt < (1u << 30) && ns > 0) {
     st = tc_alloc(ctx, &d_prev, ns);
     if (st == TC_OK) cudaMemsetAsync(d_prev, 0xFF, (size_t)ns * sizeof(uint32_t), ctx->stream);
   }
-  if (st == TC_OK) st = tc_alloc(ctx, &d_partials, (uint64_t)grid * kNumSums);
-  if (st == TC_OK) st = tc_alloc(ctx, &d_sums, kNumSums);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_partials, (uint64_t)grid * n_sums);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_sums, n_sums);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_final, 2);
   IcpState h_state{};
+  double h_final[2] = {0.0, 0.0};
   if (st == TC_OK) {
-    k_pad_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
-                                         ctx->sm_count * 8)),
-                    kIcpBlock, 0, ctx->stream>>>(d_tgt_normals_aos, nt, d_nrm);
-    ctx->launches++;
+    if (mode == kPlane) {
+      k_pad_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
+                                           ctx->sm_count * 8)),
+                      kIcpBlock, 0, ctx->stream>>>(d_tgt_normals_aos, nt, d_nrm);
+      ctx->launches++;
+    }
     k_icp_init<<<1, 1, 0, ctx->stream>>>(d_state, nullptr, init[0], init[1], init[2], init[3],
                                          init[4], init[5], init[6]);
     ctx->launches++;
     const LevelSet ls = tgt->level_set(g_tc_search_flags);
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
-      k_icp_correspond<<<grid, kIcpBlock, 0, ctx->stream>>>(ls, d_nrm, d_src, ns, max_corr_dist,
-                                                            d_state, d_partials, d_sums,
-                                                            d_match_out, d_prev);
+      if (mode == kPlane)
+        k_icp_correspond<kPlane><<<grid, kIcpBlock, 0, ctx->stream>>>(
+            ls, d_nrm, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev);
+      else
+        k_icp_correspond<kPoint><<<grid, kIcpBlock, 0, ctx->stream>>>(
+            ls, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev);
       ctx->launches++;
-      if (comm) st = tci_comm_allreduce(comm, d_sums, kNumSums);
-      k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
+      if (comm) st = tci_comm_allreduce(comm, d_sums, n_sums);
+      if (mode == kPlane)
+        k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
+      else
+        k_icp_solve_p2p<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
       ctx->launches++;
+    }
+    if (st == TC_OK && mode == kPoint) {
+      // mse of the last correspondences under the final transform (only used when not converged)
+      cudaMemsetAsync(d_final, 0, 2 * sizeof(double), ctx->stream);
+      if (ns > 0) {
+        k_icp_p2p_final_mse<<<grid, kIcpBlock, 0, ctx->stream>>>(ls, d_src, ns, d_prev, d_state,
+                                                                 d_final);
+        ctx->launches++;
+      }
+      if (comm) st = tci_comm_allreduce(comm, d_final, 2);
     }
     if (st == TC_OK && cudaGetLastError() != cudaSuccess)
       st = tc_fail(ctx, TC_GPU, "ICP kernel launch failed");
     if (st == TC_OK) {
       cudaError_t e = cudaMemcpyAsync(&h_state, d_state, sizeof(IcpState), cudaMemcpyDeviceToHost,
                                       ctx->stream);
+      if (e == cudaSuccess && mode == kPoint)
+        e = cudaMemcpyAsync(h_final, d_final, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                            ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       if (e != cudaSuccess)
         st = tc_fail(ctx, TC_GPU, std::string("ICP failed: ") + cudaGetErrorString(e));
@@ -410,17 +591,45 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
   tc_free(ctx, d_state);
   tc_free(ctx, d_partials);
   tc_free(ctx, d_sums);
+  tc_free(ctx, d_final);
   if (st != TC_OK) return st;
   if (h_state.status == 2)
     return tc_fail(ctx, TC_ALGORITHM,
-                   "Insufficient correspondences for point-to-plane ICP (need >= 6)");
+                   mode == kPlane ? "Insufficient correspondences for point-to-plane ICP (need >= 6)"
+                                  : "Insufficient correspondences found");
   if (h_state.status == 3)
-    return tc_fail(ctx, TC_ALGORITHM, "Point-to-plane system is ill-conditioned");
+    return tc_fail(ctx, TC_ALGORITHM, mode == kPlane ? "Point-to-plane system is ill-conditioned"
+                                                      : "SVD of the cross-covariance failed");
   for (int i = 0; i < 7; ++i) out->transform[i] = h_state.T[i];
-  // converged: current mse, iteration+1; otherwise previous_mse (== last mse), max_iters
-  out->mse = h_state.converged ? h_state.mse : h_state.prev_mse;
+  if (h_state.converged) {
+    out->mse = h_state.mse;
+  } else if (mode == kPlane) {
+    out->mse = h_state.prev_mse;  // previous_mse == the last iteration's mse (:595-601)
+  } else {
+    out->mse = h_final[1] > 0.0 ? (float)(h_final[0] / h_final[1]) : h_state.prev_mse;
+  }
   out->iterations = h_state.iterations;
   out->converged = h_state.converged;
   out->n_correspondences = (uint64_t)h_state.n_valid;
   return TC_OK;
+}
+
+}  // namespace
+
+extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                                            const tc_index* tgt, const float* d_tgt_normals_aos,
+                                            const float init[7], uint32_t max_iters,
+                                            float max_corr_dist, float conv_threshold,
+                                            tc_icp_result* out, uint32_t* d_match_out) {
+  return icp_device_impl(kPlane, ctx, comm, src, tgt, d_tgt_normals_aos, init, max_iters,
+                         max_corr_dist, conv_threshold, out, d_match_out);
+}
+
+extern "C" int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
+                                            const tc_index* tgt, const float init[7],
+                                            uint32_t max_iters, float max_corr_dist,
+                                            float conv_threshold, tc_icp_result* out,
+                                            uint32_t* d_match_out) {
+  return icp_device_impl(kPoint, ctx, comm, src, tgt, nullptr, init, max_iters, max_corr_dist,
+                         conv_threshold, out, d_match_out);
 }
