@@ -396,6 +396,9 @@ def bench_c3(args, tc, synth, ctx, ext, rank, world, barrier, max_over_ranks, pe
         ids = [tc.Comm.unique_id(ctx) if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         comm = tc.Comm(ctx, ids[0], world, rank)
+        handles = [None] * world          # NVLink peer buffers for the fused all-reduce
+        dist.all_gather_object(handles, comm.peer_handle())
+        comm.open_peers(handles)
     tcloud = tc.DeviceCloud(tgt, ctx)
     scloud = tc.DeviceCloud(src[lo:hi], ctx)
     d_nrm = ctx.alloc(n * 12)

@@ -181,6 +181,15 @@ int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud*
 int tc_comm_get_unique_id(tc_context* ctx, void* id_out /* TC_COMM_ID_BYTES */);
 int tc_comm_init_rank(tc_context* ctx, const void* id, int n_ranks, int rank, tc_comm** out);
 void tc_comm_destroy(tc_comm* comm);
+/* Fused all-reduce over NVLink peer memory (optional; without it the ICP falls back to
+ * ncclAllReduce + a separate solve launch).  Each rank calls tc_comm_peer_handle, the host
+ * gathers the TC_IPC_HANDLE_BYTES-byte handles of all ranks (rank order) and passes the
+ * concatenation to tc_comm_peer_open on every rank.  Afterwards the last block of the ICP
+ * correspondence kernel writes its partial normal equations straight into every peer's buffer,
+ * waits for the peers' contributions and solves — one kernel per iteration, no collective call. */
+#define TC_IPC_HANDLE_BYTES 64
+int tc_comm_peer_handle(tc_comm* comm, void* handle_out /* TC_IPC_HANDLE_BYTES */);
+int tc_comm_peer_open(tc_comm* comm, const void* all_handles /* n_ranks * TC_IPC_HANDLE_BYTES */);
 /* Sum-all-reduce of `count` f64 on the context's stream (exposed for tests). */
 int tc_comm_allreduce_f64(tc_comm* comm, double* d_buf, uint64_t count);
 

@@ -26,8 +26,17 @@ index = tc.GridIndex(tcloud, k_hint=1)
 d_nrm = ctx.alloc(n * 12)
 ctx.to_device(d_nrm, nrm)
 lo, hi = rank * n // world, (rank + 1) * n // world
-r = tc.icp_point_to_plane_device(tc.DeviceCloud(src[lo:hi], ctx), index, d_nrm, tc.IDENTITY, 20,
-                                 None, -1.0, comm)
+shard = tc.DeviceCloud(src[lo:hi], ctx)
+r_nccl = tc.icp_point_to_plane_device(shard, index, d_nrm, tc.IDENTITY, 20, None, -1.0, comm)
+# fused path: IPC-map every rank's exchange buffer, all-reduce inside the correspondence kernel
+handles = [None] * world
+dist.all_gather_object(handles, comm.peer_handle())
+comm.open_peers(handles)
+r = tc.icp_point_to_plane_device(shard, index, d_nrm, tc.IDENTITY, 20, None, -1.0, comm)
+assert np.array_equal(r.transformation, r_nccl.transformation), "fused != NCCL all-reduce"
+assert r.iterations == r_nccl.iterations and r.mse == r_nccl.mse
+rp = tc.icp_point_to_point_device(shard, index, tc.IDENTITY, 8, None, 1e-9, comm)
+assert rp.iterations >= 1 and np.isfinite(rp.transformation).all()
 # all ranks hold the identical transform
 t = torch.tensor(r.transformation, device="cuda")
 gathered = [torch.empty_like(t) for _ in range(world)]

@@ -33,6 +33,7 @@ from .api import (  # noqa: F401
     icp_point_to_point,
     icp_point_to_plane_detailed,
     icp_point_to_plane_device,
+    icp_point_to_point_device,
     k_nearest_neighbors,
     pinned_empty,
 )

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libthreecrate_cuda.so")
 TC_OK, TC_INVALID_DATA, TC_ALGORITHM, TC_GPU = 0, 1, 2, 3
 TC_NO_INDEX = 0xFFFFFFFF
 TC_COMM_ID_BYTES = 128
+TC_IPC_HANDLE_BYTES = 64
 
 
 class ThreecrateError(Exception):
@@ -87,6 +88,8 @@ SYMBOLS = {
     "tc_comm_init_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "tc_comm_destroy": (None, [_vp]),
     "tc_comm_allreduce_f64": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "tc_comm_peer_handle": (C.c_int, [_vp, _vp]),
+    "tc_comm_peer_open": (C.c_int, [_vp, _vp]),
     "tc_device_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "tc_device_free": (C.c_int, [_vp, _vp]),
     "tc_copy_to_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),

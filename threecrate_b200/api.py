@@ -456,6 +456,20 @@ class Comm:
         ctx.check(ctx.lib.tc_comm_get_unique_id(ctx.h, buf))
         return buf.raw
 
+    def peer_handle(self) -> bytes:
+        """IPC handle of this rank's NVLink exchange buffer (gather from all ranks, then
+        `open_peers`)."""
+        buf = C.create_string_buffer(_lib.TC_IPC_HANDLE_BYTES)
+        self.ctx.check(self.ctx.lib.tc_comm_peer_handle(self.h, buf))
+        return buf.raw
+
+    def open_peers(self, handles) -> None:
+        """handles: the peer_handle() of every rank, in rank order.  Enables the fused
+        (in-kernel, NVLink peer-memory) all-reduce of the ICP normal equations."""
+        blob = b"".join(handles)
+        assert len(blob) == self.n_ranks * _lib.TC_IPC_HANDLE_BYTES
+        self.ctx.check(self.ctx.lib.tc_comm_peer_open(self.h, C.create_string_buffer(blob, len(blob))))
+
     def allreduce_f64(self, dptr: int, count: int):
         self.ctx.check(self.ctx.lib.tc_comm_allreduce_f64(self.h, _vp(dptr), int(count)))
 
@@ -477,6 +491,24 @@ def icp_point_to_plane_device(src: DeviceCloud, tgt_index: GridIndex, d_tgt_norm
     res = _lib.IcpResultC()
     ctx.check(ctx.lib.tc_icp_point_to_plane_device(
         ctx.h, comm.h if comm else None, src.h, tgt_index.h, _vp(d_tgt_normals),
+        init7.ctypes.data_as(C.POINTER(C.c_float)), int(max_iters),
+        -1.0 if max_correspondence_distance is None else float(max_correspondence_distance),
+        float(convergence_threshold), C.byref(res), _vp(d_match_out) if d_match_out else None))
+    return ICPResult(np.array(res.transform[:], np.float32), float(res.mse), int(res.iterations),
+                     bool(res.converged))
+
+
+def icp_point_to_point_device(src: DeviceCloud, tgt_index: GridIndex, init=IDENTITY,
+                              max_iters: int = 50,
+                              max_correspondence_distance: Optional[float] = None,
+                              convergence_threshold: float = 1e-6, comm: Optional[Comm] = None,
+                              d_match_out: int = 0) -> ICPResult:
+    """Device-resident point-to-point ICP (tc_icp_point_to_point_device)."""
+    ctx = src.ctx
+    init7 = np.ascontiguousarray(init, np.float32).reshape(7)
+    res = _lib.IcpResultC()
+    ctx.check(ctx.lib.tc_icp_point_to_point_device(
+        ctx.h, comm.h if comm else None, src.h, tgt_index.h,
         init7.ctypes.data_as(C.POINTER(C.c_float)), int(max_iters),
         -1.0 if max_correspondence_distance is None else float(max_correspondence_distance),
         float(convergence_threshold), C.byref(res), _vp(d_match_out) if d_match_out else None))

@@ -14,6 +14,12 @@ struct tc_comm {
   tc_context* ctx = nullptr;
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // NVLink peer exchange for the fused ICP all-reduce: one small cudaMalloc'ed buffer per rank,
+  // IPC-mapped into every other rank (2 parities x n_ranks slots x 32 doubles)
+  double* xbuf = nullptr;
+  double* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peers_open = false;
+  unsigned long long epoch = 1;  // advances identically on every rank (same call sequence)
 };
 
 namespace {
@@ -88,8 +94,60 @@ extern "C" int tc_comm_init_rank(tc_context* ctx, const void* id, int n_ranks, i
   return TC_OK;
 }
 
+extern "C" int tc_comm_peer_handle(tc_comm* comm, void* handle_out) {
+  if (!comm || !handle_out) return TC_INVALID_DATA;
+  tc_context* ctx = comm->ctx;
+  if (comm->n_ranks > 8) return tc_fail(ctx, TC_INVALID_DATA, "peer exchange supports <= 8 ranks");
+  TC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!comm->xbuf) {
+    const size_t bytes = (size_t)2 * comm->n_ranks * 32 * sizeof(double);
+    TC_CUDA(ctx, cudaMalloc((void**)&comm->xbuf, bytes));
+    TC_CUDA(ctx, cudaMemset(comm->xbuf, 0, bytes));
+  }
+  cudaIpcMemHandle_t h;
+  TC_CUDA(ctx, cudaIpcGetMemHandle(&h, comm->xbuf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == TC_IPC_HANDLE_BYTES, "ipc handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  return TC_OK;
+}
+
+extern "C" int tc_comm_peer_open(tc_comm* comm, const void* all_handles) {
+  if (!comm || !all_handles) return TC_INVALID_DATA;
+  tc_context* ctx = comm->ctx;
+  if (!comm->xbuf) return tc_fail(ctx, TC_INVALID_DATA, "call tc_comm_peer_handle first");
+  TC_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < comm->n_ranks; ++r) {
+    if (r == comm->rank) {
+      comm->peer[r] = comm->xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles + (size_t)r * TC_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    TC_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    comm->peer[r] = (double*)p;
+  }
+  comm->peers_open = true;
+  return TC_OK;
+}
+
+bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
+                    unsigned long long* epoch_base, unsigned long long epochs_needed) {
+  if (!comm || !comm->peers_open) return false;
+  for (int r = 0; r < 8; ++r) peers8[r] = comm->peer[r];
+  *world = comm->n_ranks;
+  *rank = comm->rank;
+  *epoch_base = comm->epoch;
+  comm->epoch += epochs_needed;
+  return true;
+}
+
 extern "C" void tc_comm_destroy(tc_comm* comm) {
   if (!comm) return;
+  if (comm->peers_open)
+    for (int r = 0; r < comm->n_ranks; ++r)
+      if (r != comm->rank && comm->peer[r]) cudaIpcCloseMemHandle(comm->peer[r]);
+  if (comm->xbuf) cudaFree(comm->xbuf);
   if (comm->comm && nccl().ok) nccl().CommDestroy(comm->comm);
   delete comm;
 }

@@ -17,6 +17,10 @@
 
 struct tc_comm;
 int tci_comm_allreduce(tc_comm* comm, double* d_buf, uint64_t count);  // tc_comm.cu
+// peer exchange (tc_comm.cu): returns false when the communicator has no mapped peer buffers
+bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
+                    unsigned long long* epoch_base, unsigned long long epochs_needed);
+extern int g_tc_icp_fuse;  // 1 (default): fused tail; 0: separate all-reduce + solve launches
 
 namespace {
 
@@ -42,6 +46,19 @@ struct IcpState {
 struct V3 {
   float x, y, z;
 };
+
+// Fused all-reduce over NVLink peer memory (tc_comm peer exchange, tc_comm.cu): every rank's
+// exchange buffer is IPC-mapped into all ranks.  slot(parity, src) = base + (parity*world+src)*32
+// doubles: [0..28] payload, [31] epoch flag.
+struct PeerXchg {
+  double* peer[8];     // peer[r] = rank r's buffer as mapped into THIS process (peer[rank] local)
+  int world, rank;
+  unsigned long long epoch_base;
+};
+constexpr int kXSlot = 32;
+
+__device__ void icp_solve_plane(IcpState* st, const double* sums, float conv);
+__device__ void icp_solve_point(IcpState* st, const double* sums, float conv);
 __device__ __forceinline__ V3 xcross(const V3& a, const V3& b) {
   return V3{xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)),
             xsub(xmul(a.x, b.y), xmul(a.y, b.x))};
@@ -98,7 +115,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
                  const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
                  double* __restrict__ sums, uint32_t* __restrict__ match_out,
-                 uint32_t* __restrict__ prev) {
+                 uint32_t* __restrict__ prev, int fuse, PeerXchg px) {
   if (st->done) return;
   float T[7];
 #pragma unroll
@@ -201,13 +218,57 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   __syncthreads();
   if (last) {
     __threadfence();
+    double v = 0.0;
     if (threadIdx.x < NS) {
-      double v = 0.0;
       for (uint32_t b = 0; b < gridDim.x; ++b)
         v += __ldcg(&partials[(uint64_t)b * NS + threadIdx.x]);
       sums[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) st->ticket = 0;
+    if (fuse && px.world > 1) {
+      // ---- fused all-reduce: push this rank's sums into every rank's buffer, then flag --------
+      const unsigned long long epoch = px.epoch_base + st->iterations;
+      const int parity = (int)(epoch & 1ull);
+      const size_t slot = ((size_t)parity * px.world + px.rank) * kXSlot;
+      if (threadIdx.x < NS)
+        for (int r = 0; r < px.world; ++r) px.peer[r][slot + threadIdx.x] = v;
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int r = 0; r < px.world; ++r)
+          *(volatile double*)&px.peer[r][slot + kXSlot - 1] = (double)epoch;
+        // wait (bounded) until every rank's contribution for this epoch has landed here
+        const double* mine = px.peer[px.rank];
+        bool ok = true;
+        for (int r = 0; r < px.world && ok; ++r) {
+          const volatile double* f = &mine[((size_t)parity * px.world + r) * kXSlot + kXSlot - 1];
+          unsigned long long spins = 0;
+          while (*f != (double)epoch) {
+            __nanosleep(64);
+            if (++spins > (1ull << 24)) {  // ~1 s: a peer died; fail instead of hanging the GPU
+              ok = false;
+              break;
+            }
+          }
+        }
+        if (!ok) {
+          st->status = 4;
+          st->done = 1;
+        }
+      }
+      __syncthreads();
+      if (st->status == 4) return;
+      __threadfence_system();
+      if (threadIdx.x < NS) {  // sum in rank order: identical bits on every rank
+        const double* mine = px.peer[px.rank];
+        double t = 0.0;
+        for (int r = 0; r < px.world; ++r)
+          t += __ldcv(&mine[((size_t)parity * px.world + r) * kXSlot + threadIdx.x]);
+        sums[threadIdx.x] = t;
+      }
+    }
+    // (the 6x6 / Horn solve stays a separate one-thread launch: inlined here it would raise the
+    //  whole kernel to ~120 registers and halve the occupancy of the search)
   }
 }
 
@@ -294,6 +355,10 @@ __device__ void icp_apply_delta(IcpState* st, const float dq[4], const float dt[
 
 __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ sums, float conv) {
   if (threadIdx.x != 0 || st->done) return;
+  icp_solve_plane(st, sums, conv);
+}
+
+__device__ void icp_solve_plane(IcpState* st, const double* sums, float conv) {
   const double n_valid = sums[28];
   st->n_valid = n_valid;
   if (n_valid < 6.0) {  // registration.rs:568-572
@@ -359,6 +424,10 @@ __device__ void icp_apply_delta(IcpState* st, const float dq[4], const float dt[
 __global__ void k_icp_solve_p2p(IcpState* __restrict__ st, const double* __restrict__ sums,
                                 float conv) {
   if (threadIdx.x != 0 || st->done) return;
+  icp_solve_point(st, sums, conv);
+}
+
+__device__ void icp_solve_point(IcpState* st, const double* sums, float conv) {
   const double n = sums[16];
   st->n_valid = n;
   if (n < 3.0) {  // registration.rs:311-315
@@ -547,15 +616,25 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
                                          init[4], init[5], init[6]);
     ctx->launches++;
     const LevelSet ls = tgt->level_set(g_tc_search_flags);
+    // Multi-GPU: with peers mapped over NVLink the all-reduce happens inside the correspondence
+    // kernel (correspond+exchange -> solve); otherwise correspond -> ncclAllReduce -> solve.
+    PeerXchg px{};
+    px.world = 1;
+    int fuse = 0;
+    if (comm && g_tc_icp_fuse &&
+        tci_comm_peers(comm, px.peer, &px.world, &px.rank, &px.epoch_base, max_iters + 1))
+      fuse = 1;
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
       if (mode == kPlane)
         k_icp_correspond<kPlane><<<grid, kIcpBlock, 0, ctx->stream>>>(
-            ls, d_nrm, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev);
+            ls, d_nrm, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev,
+            fuse, px);
       else
         k_icp_correspond<kPoint><<<grid, kIcpBlock, 0, ctx->stream>>>(
-            ls, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev);
+            ls, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out,
+            d_prev, fuse, px);
       ctx->launches++;
-      if (comm) st = tci_comm_allreduce(comm, d_sums, n_sums);
+      if (comm && !fuse) st = tci_comm_allreduce(comm, d_sums, n_sums);
       if (mode == kPlane)
         k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
       else
@@ -597,6 +676,8 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
     return tc_fail(ctx, TC_ALGORITHM,
                    mode == kPlane ? "Insufficient correspondences for point-to-plane ICP (need >= 6)"
                                   : "Insufficient correspondences found");
+  if (h_state.status == 4)
+    return tc_fail(ctx, TC_GPU, "ICP peer exchange timed out (a rank did not arrive)");
   if (h_state.status == 3)
     return tc_fail(ctx, TC_ALGORITHM, mode == kPlane ? "Point-to-plane system is ill-conditioned"
                                                       : "SVD of the cross-covariance failed");
@@ -615,6 +696,9 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
 }
 
 }  // namespace
+
+int g_tc_icp_fuse = 1;
+extern "C" void tc_debug_set_icp_fuse(int on) { g_tc_icp_fuse = on; }
 
 extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
                                             const tc_index* tgt, const float* d_tgt_normals_aos,
