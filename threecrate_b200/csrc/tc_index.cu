@@ -5,9 +5,33 @@
 // All kernels are HBM-bound streaming passes (coalesced loads, grid sized in multiples of the SM
 // count).  Algorithmic bytes per point: bbox 12, keys+histogram 12r+4w, radix passes
 // (8r+8w) x P with P = ceil(key_bits/8), gather 4r+12r+16w, cell-range scan 8 B/cell.
+#include <chrono>
+#include <cstdlib>
+
 #include "tc_internal.cuh"
 
 namespace {
+
+// TC_TRACE=1: print host-side phase timings of tc_index_build (adds stream syncs; debug only)
+struct PhaseTrace {
+  bool on;
+  tc_context* ctx;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTrace(tc_context* c) : on(std::getenv("TC_TRACE") != nullptr), ctx(c) {
+    if (on) {
+      cudaStreamSynchronize(ctx->stream);
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tc_index_build] %-22s %8.1f us\n", what,
+            std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 constexpr int kThreads = 256;
 
@@ -73,7 +97,12 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict_
     const int cz = cell_coord(xyz[3 * (uint64_t)i + 2], g.oz, g.inv, g.nz, u);
     const uint32_t c = cell_id(g, cx, cy, cz);
     keys[i] = c;
-    if (MODE == 0) atomicAdd(&counts[c], 1u);
+    if (MODE == 0) {
+      // warp-aggregated: consecutive points of a scan usually share a cell, and coarse levels
+      // funnel thousands of points into one counter
+      const uint32_t peers = __match_any_sync(__activemask(), c);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[c], (uint32_t)__popc(peers));
+    }
   }
 }
 
@@ -116,13 +145,23 @@ __global__ void __launch_bounds__(kThreads) k_scatter_cells(const float* __restr
     const float* p = xyz + 3 * (uint64_t)i;
     const uint32_t c = keys[i];
     // the histogram itself is the cursor: it counts down to zero while the cell fills up
-    const uint32_t pos = __ldg(&cell_start[c]) + atomicSub(&counts[c], 1u) - 1u;
+    // (warp-aggregated: one atomic per distinct cell per warp)
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, c);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t old = 0;
+    if (lane == leader) old = atomicSub(&counts[c], (uint32_t)__popc(peers));
+    old = __shfl_sync(active, old, leader);
+    const uint32_t pos = __ldg(&cell_start[c]) + old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
     out[pos] = make_float4(p[0], p[1], p[2], __uint_as_float(i));
   }
 }
 
 // ---------------------------------------------------------------------- exclusive scan (u32)
-// reduce-then-scan: tile sums -> scan of tile sums (one block) -> per-tile exclusive scan.
+// Single-pass scan with decoupled look-back: one launch, every element read once and written
+// once (8 B/cell).  Tiles are handed out through an atomic ticket so that a tile's predecessors
+// are always already running; each tile publishes its aggregate, then walks back over earlier
+// tiles' (status, value) words until it meets an inclusive prefix.
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
@@ -155,53 +194,60 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return res;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const uint32_t* __restrict__ in,
-                                                                 uint64_t n,
-                                                                 uint32_t* __restrict__ tile_sums) {
-  __shared__ uint32_t sw[kScanThreads / 32 + 1];
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
-  uint32_t s = 0;
-#pragma unroll
-  for (int it = 0; it < kScanItems; ++it) {
-    const uint64_t i = base + (uint64_t)it * kScanThreads + threadIdx.x;
-    if (i < n) s += in[i];
-  }
-  uint32_t total;
-  block_exclusive_scan(s, sw, total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
+constexpr unsigned long long kTileAggregate = 1ull << 32, kTileInclusive = 2ull << 32;
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint32_t* __restrict__ tile_sums,
-                                                            uint32_t n_tiles) {
+// state[0] = ticket counter (as u64), state[1 + t] = (status << 32 | value) of tile t; zeroed.
+// out has n + 1 entries: out[n] = grand total.  in == out is allowed.
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_lookback(const uint32_t* in, uint64_t n, uint32_t* out, unsigned long long* state) {
   __shared__ uint32_t sw[kScanThreads / 32 + 1];
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < n_tiles; base += kScanThreads) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan(v, sw, total);
-    if (i < n_tiles) tile_sums[i] = carry + ex;
-    carry += total;
-  }
-}
-
-// out[i] = exclusive prefix; additionally out[n] = grand total (out has n + 1 entries).
-__global__ void __launch_bounds__(kScanThreads) k_scan_final(const uint32_t* __restrict__ in,
-                                                             uint64_t n,
-                                                             const uint32_t* __restrict__ tile_offs,
-                                                             uint32_t* __restrict__ out) {
-  __shared__ uint32_t sw[kScanThreads / 32 + 1];
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[0], 1ull);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t s = 0;
+  if (base + kScanItems <= n && (((uintptr_t)(in + base)) & 15) == 0) {
 #pragma unroll
-  for (int it = 0; it < kScanItems; ++it) {
-    const uint64_t i = base + it;
-    v[it] = i < n ? in[i] : 0;
-    s += v[it];
+    for (int it = 0; it < kScanItems; it += 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + base + it);
+      v[it] = q.x;
+      v[it + 1] = q.y;
+      v[it + 2] = q.z;
+      v[it + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < kScanItems; ++it) v[it] = (base + it < n) ? in[base + it] : 0u;
   }
+#pragma unroll
+  for (int it = 0; it < kScanItems; ++it) s += v[it];
   uint32_t total;
-  uint32_t ex = block_exclusive_scan(s, sw, total) + tile_offs[blockIdx.x];
+  uint32_t ex = block_exclusive_scan(s, sw, total);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = state + 1;
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      st[0] = kTileInclusive | total;
+    } else {
+      st[tile] = kTileAggregate | total;
+      __threadfence();
+      for (int64_t p = (int64_t)tile - 1; p >= 0; --p) {
+        unsigned long long w;
+        do {
+          w = st[p];
+        } while ((w >> 32) == 0);  // predecessor is running (ticket order): short spin
+        prefix += (uint32_t)w;
+        if ((w >> 32) == 2) break;
+      }
+      __threadfence();
+      st[tile] = kTileInclusive | (unsigned long long)(prefix + total);
+    }
+    s_prefix = prefix;
+  }
+  __syncthreads();
+  ex += s_prefix;
 #pragma unroll
   for (int it = 0; it < kScanItems; ++it) {
     const uint64_t i = base + it;
@@ -314,15 +360,13 @@ int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_ou
     return TC_OK;
   }
   const uint32_t n_tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
-  uint32_t* d_sums = nullptr;
-  TC_TRY(tc_alloc(ctx, &d_sums, n_tiles));
-  k_scan_tile_sums<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_sums);
+  unsigned long long* d_state = nullptr;
+  TC_TRY(tc_alloc(ctx, &d_state, (uint64_t)n_tiles + 1));
+  TC_CUDA(ctx, cudaMemsetAsync(d_state, 0, ((uint64_t)n_tiles + 1) * sizeof(unsigned long long),
+                               ctx->stream));
+  k_scan_lookback<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_out, d_state);
   TC_LAUNCHED(ctx);
-  k_scan_sums<<<1, kScanThreads, 0, ctx->stream>>>(d_sums, n_tiles);
-  TC_LAUNCHED(ctx);
-  k_scan_final<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_sums, d_out);
-  TC_LAUNCHED(ctx);
-  tc_free(ctx, d_sums);
+  tc_free(ctx, d_state);
   return TC_OK;
 }
 
@@ -502,7 +546,9 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     *out = ix;
     return TC_OK;
   }
+  PhaseTrace trace(ctx);
   int st = tci_bbox(ctx, cloud->d_xyz, n, ix->bbox_min, ix->bbox_max);
+  trace.mark("bbox");
   if (st != TC_OK) {
     delete ix;
     return st;
@@ -546,6 +592,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     tc_free(ctx, d_counts);
     d_counts = nullptr;
     st = level_histogram(ctx, cloud, g, low_thr, d_keys, &d_counts, stats);
+    trace.mark("trial histogram+stats");
     if (st != TC_OK) break;
     if (!auto_cell || trial == max_trials - 1) break;
     const float pop = (float)n / (float)std::max(1u, stats[0]);
@@ -578,9 +625,14 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   primary.max_pop = stats[1];
   st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
   tc_free(ctx, d_counts);
+  trace.mark("primary scan+scatter");
   int nl = 0;
   if (st == TC_OK && want_fine) {
-    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 0.25f, table_cap, d_keys, &ix->lv[nl]);
+    // (a sparse cloud in a big bbox would make a 4x finer dense table mostly empty cells: cap it)
+    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 0.25f,
+                           std::min<uint64_t>(table_cap, std::max<uint64_t>(16 * n, 1u << 18)),
+                           d_keys, &ix->lv[nl]);
+    trace.mark("fine level");
     if (st == TC_OK && ix->lv[nl].g.cell < g.cell * 0.9f) ++nl;  // table cap may refuse to refine
     else if (st == TC_OK) {
       tc_free(ctx, ix->lv[nl].d_pts);
@@ -592,6 +644,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   ix->lv[nl++] = primary;
   if (st == TC_OK && want_coarse) {
     st = build_extra_level(ctx, cloud, mn, mx, g.cell * 4.0f, table_cap, d_keys, &ix->lv[nl]);
+    trace.mark("coarse level");
     if (st == TC_OK) ++nl;
   }
   ix->n_levels = nl;
