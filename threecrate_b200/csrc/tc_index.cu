@@ -111,23 +111,27 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict_
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
                                                          uint64_t n_cells, uint32_t low_thr,
                                                          uint32_t* __restrict__ s) {
-  uint32_t occ = 0, mx = 0, low = 0;
+  uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t c = counts[i];
     occ += (c != 0);
     mx = max(mx, c);
-    low += (c <= low_thr) ? c : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) low[j] += (c <= (low_thr << j)) ? c : 0u;  // thresholds x1,2,4,8
   }
   for (int o = 16; o > 0; o >>= 1) {
     occ += __shfl_xor_sync(0xffffffffu, occ, o);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    low += __shfl_xor_sync(0xffffffffu, low, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) low[j] += __shfl_xor_sync(0xffffffffu, low[j], o);
   }
   if ((threadIdx.x & 31) == 0) {
     if (occ) atomicAdd(&s[8], occ);
     if (mx) atomicMax(&s[9], mx);
-    if (low) atomicAdd(&s[10], low);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (low[j]) atomicAdd(&s[10 + j], low[j]);
   }
 }
 
@@ -467,7 +471,7 @@ namespace {
 
 // histogram of `cloud` on grid g (+ keys); returns occupied / max_pop / low-population points
 int level_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t low_thr,
-                    uint32_t* d_keys, uint32_t** d_counts_out, uint32_t stats[3]) {
+                    uint32_t* d_keys, uint32_t** d_counts_out, uint32_t stats[6]) {
   const uint64_t n = cloud->n;
   const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
   uint32_t* d_counts = nullptr;
@@ -477,16 +481,14 @@ int level_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
       cloud->d_xyz, (uint32_t)n, g, d_keys, d_counts);
   TC_LAUNCHED(ctx);
   if (stats) {
-    TC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 8, 0, 3 * sizeof(uint32_t), ctx->stream));
+    TC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 8, 0, 6 * sizeof(uint32_t), ctx->stream));
     k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
         d_counts, n_cells, low_thr, ctx->d_scratch);
     TC_LAUNCHED(ctx);
-    TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 3 * sizeof(uint32_t),
+    TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 6 * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    stats[0] = ctx->h_scratch[8];
-    stats[1] = ctx->h_scratch[9];
-    stats[2] = ctx->h_scratch[10];
+    for (int j = 0; j < 6; ++j) stats[j] = ctx->h_scratch[8 + j];
   }
   *d_counts_out = d_counts;
   return TC_OK;
@@ -584,28 +586,32 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     if (emax > 0 && cell < emax * 1e-6) cell = (float)(emax * 1e-6);
   }
   GridParams g{};
-  uint32_t stats[3] = {0, 0, 0};
-  const int max_trials = auto_cell ? 4 : 1;
-  for (int trial = 0; trial < max_trials; ++trial) {
-    g = make_grid(mn, mx, cell, n, table_cap);
-    cell = g.cell;
-    tc_free(ctx, d_counts);
-    d_counts = nullptr;
-    st = level_histogram(ctx, cloud, g, low_thr, d_keys, &d_counts, stats);
-    trace.mark("trial histogram+stats");
-    if (st != TC_OK) break;
-    if (!auto_cell || trial == max_trials - 1) break;
-    const float pop = (float)n / (float)std::max(1u, stats[0]);
-    if (pop > target * 0.5f && pop < target * 2.0f) break;
-    // rescale assuming surface-like scaling (occupied cells ~ cell^-2); clamp the step
-    float scale = std::sqrt(target / pop);
+  uint32_t stats[6] = {0, 0, 0, 0, 0, 0};
+  // One measured trial (histogram + stats + one host sync).  If the mean population of occupied
+  // cells is off target the cell is rescaled ONCE (surface-like scaling: occupied ~ cell^-2) and
+  // re-histogrammed without waiting for new statistics; the level decisions below use the
+  // measured trial's skew, which is scale-free.
+  float stat_scale = 1.0f;  // final cell / measured cell
+  g = make_grid(mn, mx, cell, n, table_cap);
+  cell = g.cell;
+  st = level_histogram(ctx, cloud, g, low_thr, d_keys, &d_counts, stats);
+  trace.mark("trial histogram+stats");
+  float pop1 = (float)n / (float)std::max(1u, stats[0]);
+  if (st == TC_OK && auto_cell && !(pop1 > target * 0.7f && pop1 < target * 1.4f)) {
+    float scale = std::sqrt(target / pop1);
     scale = std::min(4.0f, std::max(0.25f, scale));
     float next = cell * scale;
     if (emax > 0 && next > emax) next = (float)emax;
-    if (std::fabs(next - cell) < 1e-3f * cell) break;
-    GridParams probe = make_grid(mn, mx, next, n, table_cap);  // table capacity may stop refinement
-    if (probe.cell == cell) break;
-    cell = next;
+    const GridParams g2 = make_grid(mn, mx, next, n, table_cap);
+    if (std::fabs(g2.cell - cell) > 1e-3f * cell) {
+      tc_free(ctx, d_counts);
+      d_counts = nullptr;
+      st = level_histogram(ctx, cloud, g2, 0, d_keys, &d_counts, nullptr);
+      stat_scale = g2.cell / cell;
+      g = g2;
+      cell = g2.cell;
+      trace.mark("rescaled histogram");
+    }
   }
   if (st != TC_OK) {
     tc_free(ctx, d_keys);
@@ -613,16 +619,28 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     delete ix;
     return st;
   }
+  // statistics of the final grid, extrapolated from the measured one when it was rescaled
+  const float s2 = stat_scale * stat_scale;
+  const uint32_t occ_est = (uint32_t)std::max(1.0f, (float)stats[0] / s2);
+  const uint32_t maxpop_est = (uint32_t)std::min<double>(
+      (double)n, std::ceil((double)stats[1] * std::max(1.0f, s2 * stat_scale)));
+  // skew of the measured trial: densest cell vs mean, and share of points in near-empty cells
+  const float skew = (float)stats[1] / std::max(1.0f, pop1);
+  const float target_ratio = 6.0f;
+  // "near-empty" is judged at the measured cell size: a cell pop1/target times more populated
+  // than intended needs a proportionally higher threshold (counters exist for x1, x2, x4, x8)
+  int lj = 0;
+  for (float r = pop1 / target; r >= 1.5f && lj < 3; r *= 0.5f) ++lj;
+  const uint32_t low_pts = stats[2 + lj];
   // Density skew -> extra resolutions: a 4x finer grid when some cells are far
   // over target (dense LiDAR near field), a 4x coarser one when a visible share of the points
   // sits in nearly empty cells (far field: ring growth would otherwise walk thousands of rows).
-  const bool want_fine = auto_cell && g_tc_max_levels > 1 && (float)stats[1] > 6.0f * target &&
-                         n > 4096;
+  const bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
   const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
-                           low_thr > 0 && (double)stats[2] > 0.01 * (double)n && n > 4096;
+                           low_thr > 0 && (double)low_pts > 0.01 * (double)n && n > 4096;
   GridLevel primary{};
-  primary.occupied = stats[0];
-  primary.max_pop = stats[1];
+  primary.occupied = occ_est;
+  primary.max_pop = maxpop_est;
   st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
   tc_free(ctx, d_counts);
   trace.mark("primary scan+scatter");
