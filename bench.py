@@ -270,8 +270,8 @@ def main():
     achieved = BYTES_NORMALS_PER_PT * n / kern_s / 1e9
     roofline = {"bound": "hbm", "kernel": "k_normals2<32> (fused two-pass kNN + covariance + eigen + orientation; incl. the tie-list launch)",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "peak_kind": f"of {peak_kind}", "traffic": 6.13e6,
-                "traffic_source": "profiles/r01b_p2_c2_normals_raw.csv (ncu --set full, dram read+write per launch)",
+                "peak_kind": f"of {peak_kind}", "traffic": 4.85e6,
+                "traffic_source": "profiles/r01b_c2_normals_raw.csv (ncu --set full, dram read+write per launch)",
                 "algorithmic_bytes_per_launch": BYTES_NORMALS_PER_PT * n,
                 "kernel_ms": 1e3 * kern_s, "index_build_ms": float(np.mean(ms_index)),
                 "note": "C2 (1.4 MB) is L2-resident and issue-bound, not HBM-bound; see DESIGN.md"}
