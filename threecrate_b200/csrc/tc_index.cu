@@ -525,6 +525,8 @@ int build_extra_level(tc_context* ctx, const tc_cloud* cloud, const float mn[3],
 }  // namespace
 
 int g_tc_max_levels = kMaxLevels;
+uint64_t g_tc_fine_cap = 64;  // fine-level table cap, cells per point
+extern "C" void tc_debug_set_fine_cap(int cells_per_point) { g_tc_fine_cap = (uint64_t)cells_per_point; }
 extern "C" void tc_debug_set_max_levels(int n) {
   g_tc_max_levels = n < 1 ? 1 : (n > kMaxLevels ? kMaxLevels : n);
 }
@@ -648,7 +650,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   if (st == TC_OK && want_fine) {
     // (a sparse cloud in a big bbox would make a 4x finer dense table mostly empty cells: cap it)
     st = build_extra_level(ctx, cloud, mn, mx, g.cell * 0.25f,
-                           std::min<uint64_t>(table_cap, std::max<uint64_t>(16 * n, 1u << 18)),
+                           std::min<uint64_t>(table_cap, std::max<uint64_t>(g_tc_fine_cap * n, 1u << 18)),
                            d_keys, &ix->lv[nl]);
     trace.mark("fine level");
     if (st == TC_OK && ix->lv[nl].g.cell < g.cell * 0.9f) ++nl;  // table cap may refuse to refine

@@ -26,44 +26,45 @@ using namespace tcs;
 //   pass 2  re-scan the rows that can hold d2 <= tau, append each member's position to s_a
 //           (a 4-instruction append, so lanes that accept different candidates cost little)
 //   rank    uniform loop over the n members: slot = #{v[i] < d2}; s_b[slot] = position
-template <int L>
+template <int L, bool X>
 __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, float qy, float qz,
                                                uint32_t need, uint32_t (*s_a)[kBlock],
-                                               uint32_t (*s_b)[kBlock], int& level) {
-  SelF<L> sel;
-  sel.pad = L - (int)need;
+                                               uint32_t (*s_b)[kBlock], int& level,
+                                               uint32_t* dbg = nullptr) {
+  constexpr int T = SelF<L, X>::kSlots;  // rows of s_a / s_b
+  SelF<L, X> sel;
+  sel.pad = T - (int)need;
   const int R = level_search(ls, qx, qy, qz, need, sel, level);
   const GridParams& g = ls.g[level];
   const float4* __restrict__ pts = ls.pts[level];
   const uint32_t* __restrict__ cell_start = ls.cs[level];
   const float tau = sel.kth();  // +inf when fewer than `need` points exist: everything is kept
+  if (dbg) {
+    dbg[4] = (uint32_t)clock64();
+    dbg[6] = (uint32_t)R;
+  }
   uint32_t n = 0;
   grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t j = lo; j < hi; ++j) {
       const float4 c = __ldg(&pts[j]);
       const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
       if (d2 <= tau) {
-        if (n < (uint32_t)L) s_a[n][threadIdx.x] = j;
+        if (n < (uint32_t)T) s_a[n][threadIdx.x] = j;
         ++n;
       }
     }
   });
-  if (n > (uint32_t)L) return -1;  // more ties than the table holds: exact chain kernel instead
+  if (n > (uint32_t)T) return -1;  // more ties than the table holds: exact chain kernel instead
   // rank placement.  A member whose d2 is unique lands at #{v[i] < d2}.  Bit-equal d2 (inside
   // the list, or at the K-th distance when more than `need` points are at or below it) are
   // ordered by original index: such a member also counts the equal members with a smaller index.
-  bool any_tie = n > need;  // tie straddling rank `need`
-#pragma unroll
-  for (int i = 0; i + 1 < L; ++i)
-    if (sel.v[i] == sel.v[i + 1] && sel.v[i] >= 0.0f && sel.v[i] < INFINITY) any_tie = true;
+  const bool any_tie = n > need /* tie straddling rank `need` */ || sel.has_equal();
 #pragma unroll 1
   for (uint32_t m = 0; m < n; ++m) {
     const uint32_t j = s_a[m][threadIdx.x];
     const float4 c = __ldg(&pts[j]);
     const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
-    int rank = -sel.pad;  // the sentinels are always below d2
-#pragma unroll
-    for (int i = 0; i < L; ++i) rank += (sel.v[i] < d2) ? 1 : 0;
+    int rank = sel.count_below(d2) - sel.pad;  // the sentinels are always below d2
     if (any_tie) {  // rare: order bit-equal d2 by original index
       const uint32_t id = __float_as_uint(c.w);
       for (uint32_t o = 0; o < n; ++o) {
@@ -73,6 +74,7 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
     }
     if (rank < (int)need) s_b[rank][threadIdx.x] = j;
   }
+  if (dbg) dbg[5] = (uint32_t)clock64();
   if (n > need) n = need;
   return (int)n;
 }
@@ -201,19 +203,19 @@ k_knn(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_
 // Two-pass kernel: pass 1 finds the exact K-th squared distance with the float selection list,
 // pass 2 re-scans and collects the (d2, index) keys with d2 <= tau into shared memory, which a
 // single u64 bitonic sort then orders.  More than L members (ties) -> fallback list.
-template <int L>
+template <int L, bool X>
 __global__ void __launch_bounds__(kBlock)
 k_knn2(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end,
        uint32_t k, uint32_t need, int drop_self, uint32_t* __restrict__ idx_out,
        float* __restrict__ dist_out, uint32_t* __restrict__ count_out,
        uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
-  __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
+  __shared__ uint32_t s_a[L + (X ? 1 : 0)][kBlock], s_b[L + (X ? 1 : 0)][kBlock];
   const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
   if (qi >= q_end) return;
   const float4 q = __ldg(&queries[qi]);
   const uint32_t qid = __float_as_uint(q.w);
   int level;
-  const int n = select_two_pass<L>(ls, q.x, q.y, q.z, need, s_a, s_b, level);
+  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, need, s_a, s_b, level);
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
@@ -402,28 +404,37 @@ k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t
     int level;
     const int R = level_search(ls, q.x, q.y, q.z, k + 1, tk, level);
     normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
-    if (dbg) {  // per-query cycles and final block radius (tools/kbench.py --dbg)
-      dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
-      dbg[2 * (size_t)qid + 1] = (uint32_t)R | ((uint32_t)level << 16);
+    if (dbg) {  // per-query cycles and final block radius (tools/qclock.py)
+      dbg[8 * (size_t)qid] = (uint32_t)(clock64() - t0);
+      dbg[8 * (size_t)qid + 1] = (uint32_t)R | ((uint32_t)level << 16);
     }
   }
 }
 
-template <int L>
+template <int L, bool X>
 __global__ void __launch_bounds__(kBlock)
 k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, uint32_t own_end,
            uint32_t k, int orient, float vpx, float vpy, float vpz, float* __restrict__ out,
            uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
            uint32_t* __restrict__ dbg) {
-  __shared__ uint32_t s_a[L][kBlock], s_b[L][kBlock];
+  __shared__ uint32_t s_a[L + (X ? 1 : 0)][kBlock], s_b[L + (X ? 1 : 0)][kBlock];
   const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
   if (qi >= q_end) return;
   const float4 q = __ldg(&ls.pts[0][qi]);
   if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   const uint32_t qid = __float_as_uint(q.w);
   const long long t0 = dbg ? clock64() : 0;
+  if (dbg) {  // 8 words per query (tools/qclock.py): cycles, n|level, sorted position, start ns,
+              // clock after pass 1, clock after pass 2 + rank, final block radius, start clock
+    dbg += 8 * (size_t)qid;
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    dbg[2] = qi;
+    dbg[3] = (uint32_t)ns;
+    dbg[7] = (uint32_t)t0;
+  }
   int level;
-  const int n = select_two_pass<L>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level);
+  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, dbg);
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
@@ -431,8 +442,8 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
                out);
   if (dbg) {
-    dbg[2 * (size_t)qid] = (uint32_t)(clock64() - t0);
-    dbg[2 * (size_t)qid + 1] = (uint32_t)n | ((uint32_t)level << 16);
+    dbg[0] = (uint32_t)(clock64() - t0);
+    dbg[1] = (uint32_t)n | ((uint32_t)level << 16);
   }
 }
 
@@ -545,8 +556,8 @@ inline int pick_size(uint32_t need) {
 
 }  // namespace
 
-int g_tc_search_flags = 7;
-static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (2 u32 / point)
+int g_tc_search_flags = 15;
+static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (8 u32 / point)
 extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
 extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint32_t*)d_buf; }
 
@@ -570,7 +581,17 @@ extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint3
     default: break;                                 \
   }
 
-// flags bit 2 (value 4): two-pass float selection (k_knn2 / k_normals2) when need <= 32.
+// flags bit 2 (value 4): two-pass float selection (k_knn2 / k_normals2) when need <= 33.
+// flags bit 3 (value 8): need == 17 / 33 use the 16- / 32-wide list plus one scalar slot.
+// Returns the selection shape (list slots) for `need`, 0 when the two-pass kernels do not apply.
+static int two_pass_shape(uint32_t need, int flags) {
+  if (!(flags & 4) || need < 2) return 0;
+  if (need <= 16) return 16;
+  if (need == 17 && (flags & 8)) return 17;
+  if (need <= 32) return 32;
+  if (need == 33 && (flags & 8)) return 33;
+  return 0;
+}
 int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_sorted,
                    uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out) {
@@ -583,7 +604,7 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
   int flags = g_tc_search_flags;
-  const bool two_pass = (flags & 4) && need <= 32 && need >= 2;
+  const bool two_pass = two_pass_shape(need, flags) != 0;
   if (two_pass) flags |= 2;  // pruning is always worth it with the batch scan
   const LevelSet ls = ix->level_set(flags);
   if (self_query) d_queries_sorted = ix->lv[0].d_pts;
@@ -597,14 +618,17 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions that overflowed on ties
   TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
-  if (need <= 16)
-    k_knn2<16><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,
-                                                 (uint32_t)q_end, k, need, drop_self, d_idx_out,
-                                                 d_dist_out, d_count_out, d_fb + 1, d_fb);
-  else
-    k_knn2<32><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,
-                                                 (uint32_t)q_end, k, need, drop_self, d_idx_out,
-                                                 d_dist_out, d_count_out, d_fb + 1, d_fb);
+#define TC_KNN2(LL, XX)                                                                       \
+  k_knn2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,   \
+                                                   (uint32_t)q_end, k, need, drop_self,       \
+                                                   d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)
+  switch (two_pass_shape(need, flags)) {
+    case 16: TC_KNN2(16, false); break;
+    case 17: TC_KNN2(16, true); break;
+    case 32: TC_KNN2(32, false); break;
+    default: TC_KNN2(32, true); break;
+  }
+#undef TC_KNN2
   TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_knn<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
@@ -630,7 +654,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
   int flags = g_tc_search_flags;
-  const bool two_pass = (flags & 4) && k + 1 <= 32;
+  const bool two_pass = two_pass_shape(k + 1, flags) != 0;
   if (two_pass) flags |= 2;
   const LevelSet ls = ix->level_set(flags);
   if (!two_pass) {
@@ -644,14 +668,17 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   uint32_t* d_fb = nullptr;
   TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
-  if (k + 1 <= 16)
-    k_normals2<16><<<grid, kBlock, 0, ctx->stream>>>(ls, (uint32_t)q_begin, (uint32_t)q_end,
-                                                     own_begin, own_end, k, orient, vp[0], vp[1],
-                                                     vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
-  else
-    k_normals2<32><<<grid, kBlock, 0, ctx->stream>>>(ls, (uint32_t)q_begin, (uint32_t)q_end,
-                                                     own_begin, own_end, k, orient, vp[0], vp[1],
-                                                     vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg);
+#define TC_NORMALS2(LL, XX)                                                                  \
+  k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
+      ls, (uint32_t)q_begin, (uint32_t)q_end, own_begin, own_end, k, orient, vp[0], vp[1],   \
+      vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg)
+  switch (two_pass_shape(k + 1, flags)) {
+    case 16: TC_NORMALS2(16, false); break;
+    case 17: TC_NORMALS2(16, true); break;
+    case 32: TC_NORMALS2(32, false); break;
+    default: TC_NORMALS2(32, true); break;
+  }
+#undef TC_NORMALS2
   TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(

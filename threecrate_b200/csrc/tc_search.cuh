@@ -135,21 +135,51 @@ __device__ __forceinline__ void bitonic_sort_u64(uint64_t (&a)[N]) {
 // Candidates are taken L at a time; a batch holding something below the current K-th distance
 // is sorted and merged:  m[i] = min(v[i], b[L-1-i]) keeps the L smallest of the 2L and is
 // bitonic -> log2(L) merge stages.  A float compare-exchange is 2 FMNMX, branch-free.
-template <int L>
+template <int L, bool X = false>
 struct SelF {
+  // X adds one scalar slot `x` ranked after v[L-1] (the (L+1)-th smallest): k = 16 needs 17
+  // entries, and a 16-wide network plus one min-reduction is far cheaper than the 32-wide one.
+  static constexpr int kSlots = L + (X ? 1 : 0);
   float v[L];
-  int pad;  // L - need
+  float x;
+  int pad;  // kSlots - need
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < L; ++i) v[i] = (i < pad) ? -1.0f : INFINITY;
+    x = INFINITY;
   }
-  __device__ __forceinline__ bool full() const { return v[L - 1] < INFINITY; }
-  __device__ __forceinline__ float kth() const { return v[L - 1]; }
+  __device__ __forceinline__ float kth() const { return X ? x : v[L - 1]; }
+  __device__ __forceinline__ bool full() const { return kth() < INFINITY; }
   __device__ __forceinline__ void merge(float (&b)[L]) {
     bitonic_sort_f<L>(b);
+    if (X) {
+      // the L discarded values are max(v[i], b[L-1-i]); their minimum is the (L+1)-th smallest
+      // of v u b, and every kept value is <= v[L-1] <= x, so x only competes with that minimum
+      float dm = INFINITY;
+#pragma unroll
+      for (int i = 0; i < L; ++i) dm = fminf(dm, fmaxf(v[i], b[L - 1 - i]));
+      x = fminf(x, dm);
+    }
 #pragma unroll
     for (int i = 0; i < L; ++i) v[i] = fminf(v[i], b[L - 1 - i]);
     bitonic_merge_f<L>(v);
+  }
+  // number of list entries strictly below d2 (sentinels included)
+  __device__ __forceinline__ int count_below(float d2) const {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) r += (v[i] < d2) ? 1 : 0;
+    if (X) r += (x < d2) ? 1 : 0;
+    return r;
+  }
+  // true when two real entries are bit-equal
+  __device__ __forceinline__ bool has_equal() const {
+    bool t = false;
+#pragma unroll
+    for (int i = 0; i + 1 < L; ++i)
+      if (v[i] == v[i + 1] && v[i] >= 0.0f && v[i] < INFINITY) t = true;
+    if (X && v[L - 1] == x && x < INFINITY) t = true;
+    return t;
   }
   __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
                                        float qx, float qy, float qz, int) {
@@ -169,7 +199,7 @@ struct SelF {
         b[t] = (base + t <= last) ? d : INFINITY;
         bm = fminf(bm, b[t]);
       }
-      if (bm < v[L - 1]) merge(b);  // strict: a candidate equal to the K-th distance cannot lower it
+      if (bm < kth()) merge(b);  // strict: a candidate equal to the K-th distance cannot lower it
     }
   }
 };
@@ -321,17 +351,48 @@ __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __
   return R;
 }
 
-// Multi-resolution driver.  Start at the finest level whose own cell holds at least 0.4 `need`
-// points (two table loads per level), search its 3x3x3 block, and restart on the next coarser
-// level while that block does not even hold `need` points; only the coarsest level keeps
-// doubling its radius when starved.
+// Number of indexed points in the 3x3x3 block of cells around the query (9 row look-ups).
+__device__ __forceinline__ uint32_t block_population(const GridParams& g,
+                                                     const uint32_t* __restrict__ cell_start,
+                                                     float qx, float qy, float qz) {
+  float u;
+  const int cx = cell_coord(qx, g.ox, g.inv, g.nx, u);
+  const int cy = cell_coord(qy, g.oy, g.inv, g.ny, u);
+  const int cz = cell_coord(qz, g.oz, g.inv, g.nz, u);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  uint32_t pop = 0;
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int z = min(max(cz + dz, 0), g.nz - 1), y = min(max(cy + dy, 0), g.ny - 1);
+      const bool in = (z == cz + dz) && (y == cy + dy);
+      const uint32_t row = cell_id(g, 0, y, z);
+      const uint32_t a = __ldg(&cell_start[row + x0]), b = __ldg(&cell_start[row + x1 + 1]);
+      pop += in ? (b - a) : 0u;
+    }
+  }
+  return pop;
+}
+
+// Multi-resolution driver.  Start at the finest level whose 3x3x3 block around the query holds
+// at least `need` points (flags bit 4; otherwise: whose own cell holds 0.4 `need`), search it,
+// and restart on the next coarser level while the block does not even hold `need` points; only
+// the coarsest level keeps doubling its radius when starved.  The block test matters on skewed
+// clouds: a stray point above dense ground has sparse own cells at every level and would
+// otherwise search 27 of the coarsest cells - thousands of candidates, and its whole warp waits.
 template <class Acc>
 __device__ __forceinline__ int level_search(const LevelSet& ls, float qx, float qy, float qz,
                                             uint32_t need, Acc& tk, int& level,
                                             int start_level = -1) {
   int l = start_level >= 0 ? start_level : 0;
+  const bool by_block = (ls.g[0].flags & 16) != 0;
   for (; start_level < 0 && l < ls.n - 1; ++l) {
     const GridParams& g = ls.g[l];
+    if (by_block) {
+      if (block_population(g, ls.cs[l], qx, qy, qz) >= need) break;
+      continue;
+    }
     float u;
     const int cx = cell_coord(qx, g.ox, g.inv, g.nx, u);
     const int cy = cell_coord(qy, g.oy, g.inv, g.ny, u);

@@ -18,11 +18,15 @@ ap.add_argument("--what", default="c2,c4,c3")
 ap.add_argument("--c4n", type=int, default=2_000_000)
 ap.add_argument("--cellscale", default="1.0")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--finecap", type=int, default=0)
 a = ap.parse_args()
 ctx = tc.default_context()
 lib = _lib.load()
 setflags = lib.tc_debug_set_search_flags
 setflags.argtypes = [C.c_int]
+if a.finecap:
+    lib.tc_debug_set_fine_cap.argtypes = [C.c_int]
+    lib.tc_debug_set_fine_cap(a.finecap)
 flags = [int(f) for f in a.flags.split(",")]
 scales = [float(s) for s in a.cellscale.split(",")]
 
@@ -44,6 +48,13 @@ def normals_case(name, pts, k):
     d_out = ctx.alloc(n * 24)
     base_index = tc.GridIndex(cloud, k_hint=k)
     auto = base_index.info()["cell_size"]
+    import time
+    bt = []
+    for _ in range(a.reps):
+        ctx.synchronize(); t0 = time.perf_counter()
+        tmp = tc.GridIndex(cloud, k_hint=k); ctx.synchronize()
+        bt.append((time.perf_counter() - t0) * 1e3); del tmp
+    print(f"{name:4s} index build {np.median(bt):.3f} ms (host clock), levels={base_index.info()['n_levels']}")
     ref = None
     for sc in scales:
         index = base_index if sc == 1.0 else tc.GridIndex(cloud, k_hint=k, cell_size=auto * sc)
