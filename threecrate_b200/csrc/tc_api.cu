@@ -16,6 +16,9 @@
 extern "C" const char* tc_version(void) { return "threecrate_cuda 0.1.0 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------ context
+extern "C" void tc_debug_set_search_flags(int flags);
+extern "C" void tc_debug_set_fine_cap(int cells_per_point);
+
 extern "C" int tc_context_create(int device, tc_context** out) {
   if (!out) return TC_INVALID_DATA;
   *out = nullptr;
@@ -37,6 +40,12 @@ extern "C" int tc_context_create(int device, tc_context** out) {
     return fail("cudaStreamCreate");
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
     return fail("cudaEventCreate");
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+      return fail("aux stream");
+  if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+    return fail("cudaEventCreate");
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (cudaMalloc((void**)&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
     return fail("cudaMalloc");
@@ -48,6 +57,9 @@ extern "C" int tc_context_create(int device, tc_context** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  // debug overrides for A/B runs of unmodified callers (tools/, bench.py)
+  if (const char* e = std::getenv("TC_SEARCH_FLAGS")) tc_debug_set_search_flags(atoi(e));
+  if (const char* e = std::getenv("TC_FINE_CAP")) tc_debug_set_fine_cap(atoi(e));
   *out = ctx;
   return TC_OK;
 }
@@ -60,6 +72,11 @@ extern "C" void tc_context_destroy(tc_context* ctx) {
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -229,26 +229,40 @@ k_scan_lookback(const uint32_t* in, uint64_t n, uint32_t* out, unsigned long lon
   for (int it = 0; it < kScanItems; ++it) s += v[it];
   uint32_t total;
   uint32_t ex = block_exclusive_scan(s, sw, total);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // warp-wide look-back: lane j inspects predecessor (p - j); the nearest tile that already
+    // published an inclusive prefix ends the walk, the aggregates in front of it are summed
     volatile unsigned long long* st = state + 1;
+    const int lane = threadIdx.x;
     uint32_t prefix = 0;
     if (tile == 0) {
-      st[0] = kTileInclusive | total;
+      if (lane == 0) st[0] = kTileInclusive | total;
     } else {
-      st[tile] = kTileAggregate | total;
-      __threadfence();
-      for (int64_t p = (int64_t)tile - 1; p >= 0; --p) {
-        unsigned long long w;
-        do {
-          w = st[p];
-        } while ((w >> 32) == 0);  // predecessor is running (ticket order): short spin
-        prefix += (uint32_t)w;
-        if ((w >> 32) == 2) break;
+      if (lane == 0) {
+        st[tile] = kTileAggregate | total;
+        __threadfence();
       }
-      __threadfence();
-      st[tile] = kTileInclusive | (unsigned long long)(prefix + total);
+      for (int64_t p = (int64_t)tile - 1; p >= 0; p -= 32) {
+        const int64_t idx = p - lane;
+        unsigned long long w = kTileInclusive;  // before tile 0: an inclusive prefix of 0
+        if (idx >= 0) {
+          do {
+            w = st[idx];
+          } while ((w >> 32) == 0);  // predecessor is running (ticket order): short spin
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+        const int first = incl ? (__ffs(incl) - 1) : 31;
+        uint32_t val = lane <= first ? (uint32_t)w : 0u;
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        prefix += val;
+        if (incl) break;
+      }
+      if (lane == 0) {
+        __threadfence();
+        st[tile] = kTileInclusive | (unsigned long long)(prefix + total);
+      }
     }
-    s_prefix = prefix;
+    if (lane == 0) s_prefix = prefix;
   }
   __syncthreads();
   ex += s_prefix;
@@ -512,13 +526,24 @@ int level_finish(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, ui
   return st;
 }
 
-int build_extra_level(tc_context* ctx, const tc_cloud* cloud, const float mn[3], const float mx[3],
-                      float cell, uint64_t table_cap, uint32_t* d_keys, GridLevel* lv) {
+// One extra resolution, issued on side stream `aux` (allocations included: stream-ordered memory
+// may be used on any stream once the join event orders it).
+int build_extra_level(tc_context* ctx, int aux, const tc_cloud* cloud, const float mn[3],
+                      const float mx[3], float cell, uint64_t table_cap, GridLevel* lv) {
+  cudaStream_t main_stream = ctx->stream;
+  TC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[aux], ctx->ev_fork, 0));
+  ctx->stream = ctx->aux[aux];
   const GridParams g = make_grid(mn, mx, cell, cloud->n, table_cap);
+  uint32_t* d_keys = nullptr;
   uint32_t* d_counts = nullptr;
-  TC_TRY(level_histogram(ctx, cloud, g, 0, d_keys, &d_counts, nullptr));
-  const int st = level_finish(ctx, cloud, g, d_keys, d_counts, lv);
+  int st = tc_alloc(ctx, &d_keys, cloud->n);
+  if (st == TC_OK) st = level_histogram(ctx, cloud, g, 0, d_keys, &d_counts, nullptr);
+  if (st == TC_OK) st = level_finish(ctx, cloud, g, d_keys, d_counts, lv);
   tc_free(ctx, d_counts);
+  tc_free(ctx, d_keys);
+  if (st == TC_OK && cudaEventRecord(ctx->ev_join[aux], ctx->stream) != cudaSuccess)
+    st = tc_fail(ctx, TC_GPU, "event record failed");
+  ctx->stream = main_stream;
   return st;
 }
 
@@ -640,42 +665,57 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   const bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
   const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
                            low_thr > 0 && (double)low_pts > 0.01 * (double)n && n > 4096;
+  // The extra resolutions only depend on the bbox and the decisions above: they are issued on the
+  // two side streams first and run concurrently with the primary scan + scatter.
+  GridLevel fine{}, coarse{};
+  bool have_fine = false, have_coarse = false;
+  if (want_fine || want_coarse) TC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  if (want_fine) {
+    // (a sparse cloud in a big bbox would make a 4x finer dense table mostly empty cells: cap it)
+    st = build_extra_level(ctx, 0, cloud, mn, mx, g.cell * 0.25f,
+                           std::min<uint64_t>(table_cap, std::max<uint64_t>(g_tc_fine_cap * n, 1u << 18)),
+                           &fine);
+    have_fine = true;
+  }
+  if (st == TC_OK && want_coarse) {
+    st = build_extra_level(ctx, 1, cloud, mn, mx, g.cell * 4.0f, table_cap, &coarse);
+    have_coarse = true;
+  }
   GridLevel primary{};
   primary.occupied = occ_est;
   primary.max_pop = maxpop_est;
-  st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
+  if (st == TC_OK) st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
   tc_free(ctx, d_counts);
-  trace.mark("primary scan+scatter");
+  if (have_fine) cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0);
+  if (have_coarse) cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0);
+  trace.mark("levels (concurrent)");
+  if (st != TC_OK) {  // nothing was handed to the index yet
+    cudaStreamSynchronize(ctx->stream);
+    for (GridLevel* l : {&fine, &primary, &coarse}) {
+      tc_free(ctx, l->d_pts);
+      tc_free(ctx, l->d_cell_start);
+    }
+    tc_free(ctx, d_keys);
+    delete ix;
+    return st;
+  }
   int nl = 0;
-  if (st == TC_OK && want_fine) {
-    // (a sparse cloud in a big bbox would make a 4x finer dense table mostly empty cells: cap it)
-    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 0.25f,
-                           std::min<uint64_t>(table_cap, std::max<uint64_t>(g_tc_fine_cap * n, 1u << 18)),
-                           d_keys, &ix->lv[nl]);
-    trace.mark("fine level");
-    if (st == TC_OK && ix->lv[nl].g.cell < g.cell * 0.9f) ++nl;  // table cap may refuse to refine
-    else if (st == TC_OK) {
-      tc_free(ctx, ix->lv[nl].d_pts);
-      tc_free(ctx, ix->lv[nl].d_cell_start);
-      ix->lv[nl] = GridLevel{};
+  if (have_fine) {
+    if (fine.g.cell < g.cell * 0.9f) {
+      ix->lv[nl++] = fine;
+    } else {  // the table cap refused to refine
+      tc_free(ctx, fine.d_pts);
+      tc_free(ctx, fine.d_cell_start);
     }
   }
   ix->primary = nl;
   ix->lv[nl++] = primary;
-  if (st == TC_OK && want_coarse) {
-    st = build_extra_level(ctx, cloud, mn, mx, g.cell * 4.0f, table_cap, d_keys, &ix->lv[nl]);
-    trace.mark("coarse level");
-    if (st == TC_OK) ++nl;
-  }
+  if (have_coarse) ix->lv[nl++] = coarse;
   ix->n_levels = nl;
   // finer cells nest inside primary cells (same origin, edge / 4): their population is bounded by
   // the primary maximum; the slack covers points that f32 rounding puts across a cell face
   for (int i = 0; i < nl; ++i) ix->lv[i].max_pop_bound = 2 * primary.max_pop + 32;
   tc_free(ctx, d_keys);
-  if (st != TC_OK) {
-    tc_index_free(ix);
-    return st;
-  }
   *out = ix;
   return TC_OK;
 }

@@ -16,6 +16,9 @@ struct tc_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // side streams: the extra resolutions of an index are built concurrently with the primary one
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;

@@ -556,7 +556,7 @@ inline int pick_size(uint32_t need) {
 
 }  // namespace
 
-int g_tc_search_flags = 15;
+int g_tc_search_flags = 31;
 static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (8 u32 / point)
 extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
 extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint32_t*)d_buf; }
