@@ -40,17 +40,13 @@ extern "C" int tc_context_create(int device, tc_context** out) {
     return fail("cudaStreamCreate");
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
     return fail("cudaEventCreate");
-  for (int i = 0; i < 2; ++i)
-    if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
-      return fail("aux stream");
-  if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess)
-    return fail("cudaEventCreate");
+
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (cudaMalloc((void**)&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
     return fail("cudaMalloc");
   if (cudaMallocHost((void**)&ctx->h_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
     return fail("cudaMallocHost");
+  if (tci_scratch_arm(ctx) != TC_OK) return fail("scratch init");
   // keep freed blocks cached in the stream-ordered pool: no cudaMalloc/cudaFree per call
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -72,11 +68,6 @@ extern "C" void tc_context_destroy(tc_context* ctx) {
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  for (int i = 0; i < 2; ++i) {
-    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
-    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
-  }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

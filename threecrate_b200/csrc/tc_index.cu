@@ -44,11 +44,15 @@ inline int grid_for(tc_context* ctx, uint64_t n, int per_block, int waves = 8) {
 }
 
 // ---------------------------------------------------------------------------------------- bbox
+// Scratch layout (64 words): [0..6] bbox accumulators (min x3, max x3, non-finite flag), [7] block
+// ticket, [8..13] cell statistics accumulators, [14] block ticket, [16..22] published bbox,
+// [24..29] published statistics.  The accumulators are armed once at context creation; the last
+// block of k_bbox / k_cell_stats publishes the result and re-arms them, so neither needs an
+// init launch or a memset in front (every API call on this path costs ~2-3 us of host time).
 __global__ void k_scratch_init(uint32_t* s) {
   const int t = threadIdx.x;
   if (t < 3) s[t] = 0xFFFFFFFFu;       // min (ordered encoding)
-  else if (t < 6) s[t] = 0u;           // max
-  else if (t < 64) s[t] = 0u;
+  else if (t < 64) s[t] = 0u;          // max, flags, tickets, statistics
 }
 
 __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz, uint64_t n,
@@ -82,32 +86,70 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz
     }
     if (bad) atomicOr(&s[6], 1u);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&s[7], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
+      __threadfence();
+      for (int j = 0; j < 7; ++j) s[16 + j] = atomicExch(&s[j], j < 3 ? 0xFFFFFFFFu : 0u);
+      s[7] = 0u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------- cell keys + histogram
-// MODE 0: keys + histogram (index build).  MODE 1: keys only (spatial sort of queries).
-template <int MODE>
+// Keys only (spatial sort of queries / ICP sources).
 __global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict__ xyz, uint32_t n,
-                                                        GridParams g, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ counts) {
+                                                        GridParams g, uint32_t* __restrict__ keys) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float u;
     const int cx = cell_coord(xyz[3 * (uint64_t)i + 0], g.ox, g.inv, g.nx, u);
     const int cy = cell_coord(xyz[3 * (uint64_t)i + 1], g.oy, g.inv, g.ny, u);
     const int cz = cell_coord(xyz[3 * (uint64_t)i + 2], g.oz, g.inv, g.nz, u);
-    const uint32_t c = cell_id(g, cx, cy, cz);
-    keys[i] = c;
-    if (MODE == 0) {
+    keys[i] = cell_id(g, cx, cy, cz);
+  }
+}
+
+// Up to kMaxLevels resolutions are histogrammed / scattered by ONE launch each: the point is read
+// once and its cell id recomputed per level (a dozen ALU ops; no key arrays, fewer launches).
+struct LevelJob {
+  GridParams g;
+  uint32_t* counts;            // n_cells + 1 (histogram, then scatter cursor)
+  const uint32_t* cell_start;  // n_cells + 1 (scatter only)
+  float4* out;                 // n (scatter only)
+};
+struct LevelJobs {
+  int n;
+  LevelJob l[kMaxLevels];
+};
+
+__device__ __forceinline__ uint32_t point_cell(const GridParams& g, float x, float y, float z) {
+  float u;
+  const int cx = cell_coord(x, g.ox, g.inv, g.nx, u);
+  const int cy = cell_coord(y, g.oy, g.inv, g.ny, u);
+  const int cz = cell_coord(z, g.oz, g.inv, g.nz, u);
+  return cell_id(g, cx, cy, cz);
+}
+
+__global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restrict__ xyz, uint32_t n,
+                                                          const __grid_constant__ LevelJobs jobs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = xyz[3 * (uint64_t)i + 0], y = xyz[3 * (uint64_t)i + 1],
+                z = xyz[3 * (uint64_t)i + 2];
+    const uint32_t active = __activemask();
+    for (int l = 0; l < jobs.n; ++l) {
+      const uint32_t c = point_cell(jobs.l[l].g, x, y, z);
       // warp-aggregated: consecutive points of a scan usually share a cell, and coarse levels
       // funnel thousands of points into one counter
-      const uint32_t peers = __match_any_sync(__activemask(), c);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[c], (uint32_t)__popc(peers));
+      const uint32_t peers = __match_any_sync(active, c);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+        atomicAdd(&jobs.l[l].counts[c], (uint32_t)__popc(peers));
     }
   }
 }
 
-// occupied cells -> s[8], max population -> s[9], points living in cells with population
-// <= low_thr -> s[10] (how much of the cloud is too sparse for this cell size)
+// occupied cells, max population, points living in cells with population <= low_thr x {1,2,4,8}
+// (how much of the cloud is too sparse for this cell size) -> published at s[24..29]
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
                                                          uint64_t n_cells, uint32_t low_thr,
                                                          uint32_t* __restrict__ s) {
@@ -133,31 +175,44 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
     for (int j = 0; j < 4; ++j)
       if (low[j]) atomicAdd(&s[10 + j], low[j]);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&s[14], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
+      __threadfence();
+      for (int j = 0; j < 6; ++j) s[24 + j] = atomicExch(&s[8 + j], 0u);
+      s[14] = 0u;
+    }
+  }
 }
 
-// Counting-sort scatter: point i goes to cursor[cell(i)]++ as float4 (x, y, z, bits(i)).
-// The order INSIDE a cell is arrival order (not
-// deterministic) — nothing downstream depends on it: every selection is keyed by (d2, original
-// index) and multi-GPU shards own whole cells.
-__global__ void __launch_bounds__(kThreads) k_scatter_cells(const float* __restrict__ xyz,
-                                                            const uint32_t* __restrict__ keys,
-                                                            uint32_t n,
-                                                            const uint32_t* __restrict__ cell_start,
-                                                            uint32_t* __restrict__ counts,
-                                                            float4* __restrict__ out) {
+// Counting-sort scatter: point i goes to cursor[cell(i)]++ as float4 (x, y, z, bits(i)), for
+// every level of `jobs`.  The order INSIDE a cell is arrival order (not deterministic) — nothing
+// downstream depends on it: every selection is keyed by (d2, original index) and multi-GPU
+// shards own whole cells.
+__global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __restrict__ xyz,
+                                                             uint32_t n,
+                                                             const __grid_constant__ LevelJobs jobs) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float* p = xyz + 3 * (uint64_t)i;
-    const uint32_t c = keys[i];
-    // the histogram itself is the cursor: it counts down to zero while the cell fills up
-    // (warp-aggregated: one atomic per distinct cell per warp)
+    const float x = xyz[3 * (uint64_t)i + 0], y = xyz[3 * (uint64_t)i + 1],
+                z = xyz[3 * (uint64_t)i + 2];
+    const float4 v = make_float4(x, y, z, __uint_as_float(i));
     const uint32_t active = __activemask();
-    const uint32_t peers = __match_any_sync(active, c);
-    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-    uint32_t old = 0;
-    if (lane == leader) old = atomicSub(&counts[c], (uint32_t)__popc(peers));
-    old = __shfl_sync(active, old, leader);
-    const uint32_t pos = __ldg(&cell_start[c]) + old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    out[pos] = make_float4(p[0], p[1], p[2], __uint_as_float(i));
+    const int lane = threadIdx.x & 31;
+    for (int l = 0; l < jobs.n; ++l) {
+      const LevelJob& jb = jobs.l[l];
+      const uint32_t c = point_cell(jb.g, x, y, z);
+      // the histogram itself is the cursor: it counts down to zero while the cell fills up
+      // (warp-aggregated: one atomic per distinct cell per warp)
+      const uint32_t peers = __match_any_sync(active, c);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) old = atomicSub(&jb.counts[c], (uint32_t)__popc(peers));
+      old = __shfl_sync(active, old, leader);
+      const uint32_t pos =
+          __ldg(&jb.cell_start[c]) + old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      jb.out[pos] = v;
+    }
   }
 }
 
@@ -200,15 +255,31 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 
 constexpr unsigned long long kTileAggregate = 1ull << 32, kTileInclusive = 2ull << 32;
 
-// state[0] = ticket counter (as u64), state[1 + t] = (status << 32 | value) of tile t; zeroed.
-// out has n + 1 entries: out[n] = grand total.  in == out is allowed.
+// Up to kMaxLevels independent tables scanned by one launch: tickets [tile_begin[j],
+// tile_begin[j+1]) belong to table j, whose look-back stops at its own first tile.
+struct ScanJobs {
+  int n;
+  const uint32_t* in[kMaxLevels];
+  uint32_t* out[kMaxLevels];  // n + 1 entries: out[n] = grand total.  in == out is allowed.
+  uint64_t len[kMaxLevels];
+  uint32_t tile_begin[kMaxLevels + 1];
+};
+
+// state[0] = ticket counter (as u64), state[1 + t] = (status << 32 | value) of ticket t; zeroed.
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_lookback(const uint32_t* in, uint64_t n, uint32_t* out, unsigned long long* state) {
+k_scan_lookback(const __grid_constant__ ScanJobs jobs, unsigned long long* state) {
   __shared__ uint32_t sw[kScanThreads / 32 + 1];
   __shared__ uint32_t s_tile, s_prefix;
   if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[0], 1ull);
   __syncthreads();
-  const uint32_t tile = s_tile;
+  const uint32_t ticket = s_tile;
+  int j = 0;
+  while (j + 1 < jobs.n && ticket >= jobs.tile_begin[j + 1]) ++j;
+  const uint32_t first = jobs.tile_begin[j];  // first ticket of this table
+  const uint32_t* in = jobs.in[j];
+  uint32_t* out = jobs.out[j];
+  const uint64_t n = jobs.len[j];
+  const uint32_t tile = ticket - first;
   const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t s = 0;
@@ -236,30 +307,30 @@ k_scan_lookback(const uint32_t* in, uint64_t n, uint32_t* out, unsigned long lon
     const int lane = threadIdx.x;
     uint32_t prefix = 0;
     if (tile == 0) {
-      if (lane == 0) st[0] = kTileInclusive | total;
+      if (lane == 0) st[ticket] = kTileInclusive | total;
     } else {
       if (lane == 0) {
-        st[tile] = kTileAggregate | total;
+        st[ticket] = kTileAggregate | total;
         __threadfence();
       }
-      for (int64_t p = (int64_t)tile - 1; p >= 0; p -= 32) {
+      for (int64_t p = (int64_t)ticket - 1; p >= (int64_t)first; p -= 32) {
         const int64_t idx = p - lane;
-        unsigned long long w = kTileInclusive;  // before tile 0: an inclusive prefix of 0
-        if (idx >= 0) {
+        unsigned long long w = kTileInclusive;  // before the first tile: an inclusive prefix of 0
+        if (idx >= (int64_t)first) {
           do {
             w = st[idx];
           } while ((w >> 32) == 0);  // predecessor is running (ticket order): short spin
         }
         const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
-        const int first = incl ? (__ffs(incl) - 1) : 31;
-        uint32_t val = lane <= first ? (uint32_t)w : 0u;
+        const int stop = incl ? (__ffs(incl) - 1) : 31;
+        uint32_t val = lane <= stop ? (uint32_t)w : 0u;
         for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
         prefix += val;
         if (incl) break;
       }
       if (lane == 0) {
         __threadfence();
-        st[tile] = kTileInclusive | (unsigned long long)(prefix + total);
+        st[ticket] = kTileInclusive | (unsigned long long)(prefix + total);
       }
     }
     if (lane == 0) s_prefix = prefix;
@@ -372,20 +443,40 @@ int key_bits_for(uint64_t n_cells) {
 }  // namespace
 
 // ==========================================================================================
+// `d_state` (tiles + 1 u64 words, zeroed) may be supplied by the caller; otherwise it is
+// allocated and cleared here.
+static int scan_tables(tc_context* ctx, ScanJobs& jobs, unsigned long long* d_state) {
+  uint32_t tiles = 0;
+  for (int j = 0; j < jobs.n; ++j) {
+    jobs.tile_begin[j] = tiles;
+    tiles += (uint32_t)((jobs.len[j] + kScanTile - 1) / kScanTile);
+  }
+  jobs.tile_begin[jobs.n] = tiles;
+  if (tiles == 0) return TC_OK;
+  unsigned long long* own = nullptr;
+  if (!d_state) {
+    TC_TRY(tc_alloc(ctx, &own, (uint64_t)tiles + 1));
+    TC_CUDA(ctx, cudaMemsetAsync(own, 0, ((uint64_t)tiles + 1) * sizeof(unsigned long long),
+                                 ctx->stream));
+    d_state = own;
+  }
+  k_scan_lookback<<<tiles, kScanThreads, 0, ctx->stream>>>(jobs, d_state);
+  TC_LAUNCHED(ctx);
+  tc_free(ctx, own);
+  return TC_OK;
+}
+
 int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n) {
   if (n == 0) {
     TC_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(uint32_t), ctx->stream));
     return TC_OK;
   }
-  const uint32_t n_tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
-  unsigned long long* d_state = nullptr;
-  TC_TRY(tc_alloc(ctx, &d_state, (uint64_t)n_tiles + 1));
-  TC_CUDA(ctx, cudaMemsetAsync(d_state, 0, ((uint64_t)n_tiles + 1) * sizeof(unsigned long long),
-                               ctx->stream));
-  k_scan_lookback<<<n_tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_out, d_state);
-  TC_LAUNCHED(ctx);
-  tc_free(ctx, d_state);
-  return TC_OK;
+  ScanJobs jobs{};
+  jobs.n = 1;
+  jobs.in[0] = d_in;
+  jobs.out[0] = d_out;
+  jobs.len[0] = n;
+  return scan_tables(ctx, jobs, nullptr);
 }
 
 int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_alt,
@@ -421,12 +512,16 @@ int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, ui
   return TC_OK;
 }
 
-int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]) {
+int tci_scratch_arm(tc_context* ctx) {
   k_scratch_init<<<1, 64, 0, ctx->stream>>>(ctx->d_scratch);
   TC_LAUNCHED(ctx);
+  return TC_OK;
+}
+
+int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]) {
   k_bbox<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(d_xyz, n, ctx->d_scratch);
   TC_LAUNCHED(ctx);
-  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(uint32_t),
+  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch + 16, 8 * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, ctx->stream));
   TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->h_scratch[6] != 0)
@@ -483,68 +578,33 @@ float target_population(uint32_t k_hint) {
 
 namespace {
 
-// histogram of `cloud` on grid g (+ keys); returns occupied / max_pop / low-population points
-int level_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t low_thr,
-                    uint32_t* d_keys, uint32_t** d_counts_out, uint32_t stats[6]) {
-  const uint64_t n = cloud->n;
-  const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
+inline uint64_t round_up4(uint64_t v) { return (v + 3) & ~(uint64_t)3; }
+inline uint64_t cells_of(const GridParams& g) { return (uint64_t)g.nx * g.ny * g.nz; }
+
+// Trial histogram of `cloud` on grid g plus its statistics (one host sync):
+// stats = occupied / max_pop / points in cells with population <= low_thr x {1,2,4,8}
+int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t low_thr,
+                    uint32_t** d_counts_out, uint32_t stats[6]) {
+  const uint64_t n = cloud->n, n_cells = cells_of(g);
   uint32_t* d_counts = nullptr;
   TC_TRY(tc_alloc(ctx, &d_counts, n_cells + 1));
-  TC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
-  k_cell_keys<0><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
-      cloud->d_xyz, (uint32_t)n, g, d_keys, d_counts);
-  TC_LAUNCHED(ctx);
-  if (stats) {
-    TC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 8, 0, 6 * sizeof(uint32_t), ctx->stream));
-    k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
-        d_counts, n_cells, low_thr, ctx->d_scratch);
-    TC_LAUNCHED(ctx);
-    TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 6 * sizeof(uint32_t),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int j = 0; j < 6; ++j) stats[j] = ctx->h_scratch[8 + j];
-  }
   *d_counts_out = d_counts;
+  TC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
+  LevelJobs jobs{};
+  jobs.n = 1;
+  jobs.l[0].g = g;
+  jobs.l[0].counts = d_counts;
+  k_hist_levels<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n,
+                                                                         jobs);
+  TC_LAUNCHED(ctx);
+  k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
+      d_counts, n_cells, low_thr, ctx->d_scratch);
+  TC_LAUNCHED(ctx);
+  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 24, 6 * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int j = 0; j < 6; ++j) stats[j] = ctx->h_scratch[8 + j];
   return TC_OK;
-}
-
-// counts -> cell_start (scan), then counting-sort scatter into the level's float4 array
-int level_finish(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t* d_keys,
-                 uint32_t* d_counts, GridLevel* lv) {
-  const uint64_t n = cloud->n;
-  lv->g = g;
-  lv->n_cells = (uint64_t)g.nx * g.ny * g.nz;
-  int st = tc_alloc(ctx, &lv->d_cell_start, lv->n_cells + 1);
-  if (st == TC_OK) st = tci_exclusive_scan_u32(ctx, d_counts, lv->d_cell_start, lv->n_cells);
-  if (st == TC_OK) st = tc_alloc(ctx, &lv->d_pts, n);
-  if (st == TC_OK) {
-    k_scatter_cells<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(
-        cloud->d_xyz, d_keys, (uint32_t)n, lv->d_cell_start, d_counts, lv->d_pts);
-    ctx->launches++;
-    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "scatter launch failed");
-  }
-  return st;
-}
-
-// One extra resolution, issued on side stream `aux` (allocations included: stream-ordered memory
-// may be used on any stream once the join event orders it).
-int build_extra_level(tc_context* ctx, int aux, const tc_cloud* cloud, const float mn[3],
-                      const float mx[3], float cell, uint64_t table_cap, GridLevel* lv) {
-  cudaStream_t main_stream = ctx->stream;
-  TC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[aux], ctx->ev_fork, 0));
-  ctx->stream = ctx->aux[aux];
-  const GridParams g = make_grid(mn, mx, cell, cloud->n, table_cap);
-  uint32_t* d_keys = nullptr;
-  uint32_t* d_counts = nullptr;
-  int st = tc_alloc(ctx, &d_keys, cloud->n);
-  if (st == TC_OK) st = level_histogram(ctx, cloud, g, 0, d_keys, &d_counts, nullptr);
-  if (st == TC_OK) st = level_finish(ctx, cloud, g, d_keys, d_counts, lv);
-  tc_free(ctx, d_counts);
-  tc_free(ctx, d_keys);
-  if (st == TC_OK && cudaEventRecord(ctx->ev_join[aux], ctx->stream) != cudaSuccess)
-    st = tc_fail(ctx, TC_GPU, "event record failed");
-  ctx->stream = main_stream;
-  return st;
 }
 
 }  // namespace
@@ -587,13 +647,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   const double ex = (double)mx[0] - mn[0], ey = (double)mx[1] - mn[1], ez = (double)mx[2] - mn[2];
   const double emax = std::max(ex, std::max(ey, ez));
 
-  uint32_t* d_keys = nullptr;
-  uint32_t* d_counts = nullptr;
-  st = tc_alloc(ctx, &d_keys, n);
-  if (st != TC_OK) {
-    delete ix;
-    return st;
-  }
+  uint32_t* d_trial = nullptr;  // histogram of the measured trial
   const uint64_t table_cap = std::min<uint64_t>(kMaxCells, std::max<uint64_t>(64 * n, 1u << 20));
   const float target = target_population(k_hint);
   // a 3x3x3 block of surface-like data spans ~9 occupied cells: it cannot even hold k+1 points
@@ -612,39 +666,35 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     if (emax > 0 && cell > emax) cell = (float)emax;
     if (emax > 0 && cell < emax * 1e-6) cell = (float)(emax * 1e-6);
   }
-  GridParams g{};
   uint32_t stats[6] = {0, 0, 0, 0, 0, 0};
   // One measured trial (histogram + stats + one host sync).  If the mean population of occupied
   // cells is off target the cell is rescaled ONCE (surface-like scaling: occupied ~ cell^-2) and
-  // re-histogrammed without waiting for new statistics; the level decisions below use the
-  // measured trial's skew, which is scale-free.
+  // re-histogrammed together with the extra resolutions, without waiting for new statistics;
+  // the level decisions below use the measured trial's skew, which is scale-free.
   float stat_scale = 1.0f;  // final cell / measured cell
-  g = make_grid(mn, mx, cell, n, table_cap);
+  GridParams g = make_grid(mn, mx, cell, n, table_cap);
   cell = g.cell;
-  st = level_histogram(ctx, cloud, g, low_thr, d_keys, &d_counts, stats);
+  st = trial_histogram(ctx, cloud, g, low_thr, &d_trial, stats);
   trace.mark("trial histogram+stats");
-  float pop1 = (float)n / (float)std::max(1u, stats[0]);
-  if (st == TC_OK && auto_cell && !(pop1 > target * 0.7f && pop1 < target * 1.4f)) {
+  if (st != TC_OK) {
+    tc_free(ctx, d_trial);
+    delete ix;
+    return st;
+  }
+  bool primary_counted = true;  // d_trial holds the primary histogram
+  const float pop1 = (float)n / (float)std::max(1u, stats[0]);
+  if (auto_cell && !(pop1 > target * 0.7f && pop1 < target * 1.4f)) {
     float scale = std::sqrt(target / pop1);
     scale = std::min(4.0f, std::max(0.25f, scale));
     float next = cell * scale;
     if (emax > 0 && next > emax) next = (float)emax;
     const GridParams g2 = make_grid(mn, mx, next, n, table_cap);
     if (std::fabs(g2.cell - cell) > 1e-3f * cell) {
-      tc_free(ctx, d_counts);
-      d_counts = nullptr;
-      st = level_histogram(ctx, cloud, g2, 0, d_keys, &d_counts, nullptr);
+      primary_counted = false;
       stat_scale = g2.cell / cell;
       g = g2;
       cell = g2.cell;
-      trace.mark("rescaled histogram");
     }
-  }
-  if (st != TC_OK) {
-    tc_free(ctx, d_keys);
-    tc_free(ctx, d_counts);
-    delete ix;
-    return st;
   }
   // statistics of the final grid, extrapolated from the measured one when it was rescaled
   const float s2 = stat_scale * stat_scale;
@@ -662,70 +712,107 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   // Density skew -> extra resolutions: a 4x finer grid when some cells are far
   // over target (dense LiDAR near field), a 4x coarser one when a visible share of the points
   // sits in nearly empty cells (far field: ring growth would otherwise walk thousands of rows).
-  const bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
+  bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
   const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
                            low_thr > 0 && (double)low_pts > 0.01 * (double)n && n > 4096;
-  // The extra resolutions only depend on the bbox and the decisions above: they are issued on the
-  // two side streams first and run concurrently with the primary scan + scatter.
-  GridLevel fine{}, coarse{};
-  bool have_fine = false, have_coarse = false;
-  if (want_fine || want_coarse) TC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+
+  // Level geometry, finest first.
+  GridParams lg[kMaxLevels];
+  int nl = 0, primary = 0;
   if (want_fine) {
     // (a sparse cloud in a big bbox would make a 4x finer dense table mostly empty cells: cap it)
-    st = build_extra_level(ctx, 0, cloud, mn, mx, g.cell * 0.25f,
-                           std::min<uint64_t>(table_cap, std::max<uint64_t>(g_tc_fine_cap * n, 1u << 18)),
-                           &fine);
-    have_fine = true;
+    const GridParams gf = make_grid(
+        mn, mx, g.cell * 0.25f, n,
+        std::min<uint64_t>(table_cap, std::max<uint64_t>(g_tc_fine_cap * n, 1u << 18)));
+    if (gf.cell < g.cell * 0.9f) lg[nl++] = gf;  // the table cap may refuse to refine
+    else want_fine = false;
   }
-  if (st == TC_OK && want_coarse) {
-    st = build_extra_level(ctx, 1, cloud, mn, mx, g.cell * 4.0f, table_cap, &coarse);
-    have_coarse = true;
+  primary = nl;
+  lg[nl++] = g;
+  if (want_coarse) lg[nl++] = make_grid(mn, mx, g.cell * 4.0f, n, table_cap);
+
+  // One persistent arena (cell_start tables + sorted points of every level) and one temporary
+  // arena (histograms still to be counted + scan state), cleared by a single memset: every API
+  // call costs the host 2-3 us, which is what bounds the build of a LiDAR-frame-sized cloud.
+  uint64_t words = 0, cs_off[kMaxLevels], pts_off[kMaxLevels];
+  for (int l = 0; l < nl; ++l) {
+    cs_off[l] = words;
+    words += round_up4(cells_of(lg[l]) + 1);
   }
-  GridLevel primary{};
-  primary.occupied = occ_est;
-  primary.max_pop = maxpop_est;
-  if (st == TC_OK) st = level_finish(ctx, cloud, g, d_keys, d_counts, &primary);
-  tc_free(ctx, d_counts);
-  if (have_fine) cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0);
-  if (have_coarse) cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0);
-  trace.mark("levels (concurrent)");
-  if (st != TC_OK) {  // nothing was handed to the index yet
-    cudaStreamSynchronize(ctx->stream);
-    for (GridLevel* l : {&fine, &primary, &coarse}) {
-      tc_free(ctx, l->d_pts);
-      tc_free(ctx, l->d_cell_start);
+  for (int l = 0; l < nl; ++l) {
+    pts_off[l] = words;
+    words += 4 * n;
+  }
+  uint64_t twords = 0, cnt_off[kMaxLevels], tiles = 0;
+  for (int l = 0; l < nl; ++l) {
+    tiles += (cells_of(lg[l]) + kScanTile - 1) / kScanTile;
+    if (l == primary && primary_counted) continue;
+    cnt_off[l] = twords;
+    twords += round_up4(cells_of(lg[l]) + 1);
+  }
+  const uint64_t state_off = twords;  // u64 words, 8-byte aligned since twords % 4 == 0
+  twords += 2 * (tiles + 1);
+  uint32_t* d_tmp = nullptr;
+  st = tc_alloc(ctx, &ix->d_arena, words);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_tmp, twords);
+  if (st == TC_OK &&
+      cudaMemsetAsync(d_tmp, 0, twords * sizeof(uint32_t), ctx->stream) != cudaSuccess)
+    st = tc_fail(ctx, TC_GPU, "memset failed");
+  LevelJobs all{}, todo{};
+  ScanJobs scan{};
+  if (st == TC_OK) {
+    all.n = scan.n = nl;
+    for (int l = 0; l < nl; ++l) {
+      LevelJob& jb = all.l[l];
+      jb.g = lg[l];
+      jb.counts = (l == primary && primary_counted) ? d_trial : d_tmp + cnt_off[l];
+      jb.cell_start = ix->d_arena + cs_off[l];
+      jb.out = reinterpret_cast<float4*>(ix->d_arena + pts_off[l]);
+      if (!(l == primary && primary_counted)) todo.l[todo.n++] = jb;
+      scan.in[l] = jb.counts;
+      scan.out[l] = ix->d_arena + cs_off[l];
+      scan.len[l] = cells_of(lg[l]);
     }
-    tc_free(ctx, d_keys);
-    delete ix;
+    const int grid = grid_for(ctx, n, kThreads);
+    if (todo.n > 0) {
+      k_hist_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, todo);
+      ctx->launches++;
+    }
+    st = scan_tables(ctx, scan, reinterpret_cast<unsigned long long*>(d_tmp + state_off));
+    if (st == TC_OK) {
+      k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "index build launch failed");
+    }
+  }
+  tc_free(ctx, d_tmp);
+  tc_free(ctx, d_trial);
+  trace.mark("levels: hist+scan+scatter");
+  if (st != TC_OK) {
+    tc_index_free(ix);
     return st;
   }
-  int nl = 0;
-  if (have_fine) {
-    if (fine.g.cell < g.cell * 0.9f) {
-      ix->lv[nl++] = fine;
-    } else {  // the table cap refused to refine
-      tc_free(ctx, fine.d_pts);
-      tc_free(ctx, fine.d_cell_start);
-    }
+  for (int l = 0; l < nl; ++l) {
+    GridLevel& lv = ix->lv[l];
+    lv.g = lg[l];
+    lv.n_cells = cells_of(lg[l]);
+    lv.d_cell_start = ix->d_arena + cs_off[l];
+    lv.d_pts = reinterpret_cast<float4*>(ix->d_arena + pts_off[l]);
+    // finer cells nest inside primary cells (same origin, edge / 4): their population is bounded
+    // by the primary maximum; the slack covers points that f32 rounding puts across a cell face
+    lv.max_pop_bound = 2 * maxpop_est + 32;
   }
-  ix->primary = nl;
-  ix->lv[nl++] = primary;
-  if (have_coarse) ix->lv[nl++] = coarse;
+  ix->lv[primary].occupied = occ_est;
+  ix->lv[primary].max_pop = maxpop_est;
+  ix->primary = primary;
   ix->n_levels = nl;
-  // finer cells nest inside primary cells (same origin, edge / 4): their population is bounded by
-  // the primary maximum; the slack covers points that f32 rounding puts across a cell face
-  for (int i = 0; i < nl; ++i) ix->lv[i].max_pop_bound = 2 * primary.max_pop + 32;
-  tc_free(ctx, d_keys);
   *out = ix;
   return TC_OK;
 }
 
 extern "C" void tc_index_free(tc_index* ix) {
   if (!ix) return;
-  for (int i = 0; i < kMaxLevels; ++i) {
-    tc_free(ix->ctx, ix->lv[i].d_pts);
-    tc_free(ix->ctx, ix->lv[i].d_cell_start);
-  }
+  tc_free(ix->ctx, ix->d_arena);  // the levels are views into the arena
   delete ix;
 }
 
@@ -761,8 +848,8 @@ int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const Grid
   if (st == TC_OK) st = tc_alloc(ctx, &d_vals, n);
   if (st == TC_OK) st = tc_alloc(ctx, &d_vals_alt, n);
   if (st == TC_OK) {
-    k_cell_keys<1><<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(d_xyz, (uint32_t)n, g,
-                                                                            d_keys, nullptr);
+    k_cell_keys<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(d_xyz, (uint32_t)n, g,
+                                                                         d_keys);
     ctx->launches++;
     const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
     st = tci_radix_sort_pairs(ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n,

@@ -16,9 +16,6 @@ struct tc_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // side streams: the extra resolutions of an index are built concurrently with the primary one
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -69,7 +66,8 @@ struct tc_index {
   float bbox_min[3]{}, bbox_max[3]{};
   int n_levels = 0;
   int primary = 0;                  // the level built for the requested / automatic cell size
-  GridLevel lv[kMaxLevels];         // fine -> coarse
+  GridLevel lv[kMaxLevels];         // fine -> coarse; views into d_arena
+  uint32_t* d_arena = nullptr;      // cell_start tables + sorted float4 points of every level
   LevelSet level_set(int flags) const {
     LevelSet s{};
     s.n = n_levels;
@@ -128,6 +126,7 @@ inline void tc_free(tc_context* ctx, void* p) {
 // internal entry points shared between translation units
 // ------------------------------------------------------------------------------------------
 // tc_index.cu
+int tci_scratch_arm(tc_context* ctx);  // once per context (see k_bbox)
 int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]);
 // Spatially sort arbitrary points by the cells of grid `g` (clamped): returns float4
 // (x,y,z,bits(orig idx)) in *d_sorted (caller frees with tc_free).
