@@ -120,90 +120,106 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   float T[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) T[i] = st->T[i];
-  // Per-thread partials in f32: the products a_i a_j are f32 in the reference too
-  // (registration.rs:426-427) and a thread only sums a handful of points; everything across
-  // threads (warp, block, grid) is reduced in f64.
+  // Sums: the products a_i a_j are f32 in the reference too (registration.rs:426-427).  Each
+  // trip of the loop a warp transposes-and-reduces its 32 x NS products with 31 shuffles (lane j
+  // ends up with the warp's total of sum j) and adds that to ONE f64 register per lane - instead
+  // of carrying NS accumulators per thread through the search, which cost 29 registers and a
+  // third of the occupancy.  Everything across warps, blocks and ranks is reduced in f64.
   constexpr int NS = MODE == kPlane ? kNumSums : kNumSumsP2P;
-  float acc[NS];
-#pragma unroll
-  for (int i = 0; i < NS; ++i) acc[i] = 0.0f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
 
-  for (uint32_t i = blockIdx.x * kIcpBlock + threadIdx.x; i < ns; i += gridDim.x * kIcpBlock) {
-    const float4 s4 = __ldg(&src[i]);
-    // current_transform * p  (registration.rs:540-544)
-    V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
-    s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
-    // Seed the search with last iteration's match (level << 30 | sorted position): the pose moves
-    // little between iterations, so this candidate is almost always the answer again and bounds
-    // the search to the one or two cells around the query.  Exactness is unaffected.
-    Best1 best;
-    int level, start = -1;
-    const uint32_t seed = prev ? prev[i] : 0xFFFFFFFFu;
-    if (seed != 0xFFFFFFFFu) {
-      start = (int)(seed >> 30);
-      best.pos = seed & 0x3FFFFFFFu;
-      const float4 c = __ldg(&ls.pts[start][best.pos]);
-      const float d2 = dist2_exact(c.x, c.y, c.z, s.x, s.y, s.z);
-      best.key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
-      best.seeded = true;
-    }
-    if (best.seeded) {
-      // box query around the seed distance: usually one or two rows of one or two cells
-      level = start;
-      box_visit(ls.g[level], ls.cs[level], s.x, s.y, s.z, best.kth(),
-                [&](uint32_t lo, uint32_t hi) { best.scan(ls.pts[level], lo, hi, s.x, s.y, s.z, 0); });
-    } else {
-      level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
-    }
-    bool valid = best.full();
-    if (prev) prev[i] = valid ? (((uint32_t)level << 30) | best.pos) : 0xFFFFFFFFu;
-    if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
-      if (xsqrt(best.kth()) > max_dist) valid = false;
-    }
-    if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
-    if (valid) {
-      const float4 d4 = __ldg(&ls.pts[level][best.pos]);
-      if (MODE == kPlane) {
-        const float4 n4 = __ldg(&tgt_nrm[__float_as_uint(d4.w)]);
-        const V3 n{n4.x, n4.y, n4.z};
-        const V3 c = xcross(s, n);  // registration.rs:418
-        const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
-        const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
-        const float a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int cc = r; cc < 6; ++cc)
-            acc[r * 6 - (r * (r - 1)) / 2 + (cc - r)] += xmul(a[r], a[cc]);
-#pragma unroll
-        for (int r = 0; r < 6; ++r) acc[21 + r] += xmul(a[r], b);
-        acc[27] += xmul(b, b);
-        acc[28] += 1.0f;
+  for (uint32_t i0 = blockIdx.x * kIcpBlock + warp * 32; i0 < ns; i0 += gridDim.x * kIcpBlock) {
+    const uint32_t i = i0 + lane;
+    bool valid = false;
+    V3 s{0.0f, 0.0f, 0.0f};
+    float4 d4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (i < ns) {
+      const float4 s4 = __ldg(&src[i]);
+      // current_transform * p  (registration.rs:540-544)
+      s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
+      s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
+      // Seed the search with last iteration's match (level << 30 | sorted position): the pose
+      // moves little between iterations, so this candidate is almost always the answer again and
+      // bounds the search to the one or two cells around the query.  Exactness is unaffected.
+      Best1 best;
+      int level, start = -1;
+      const uint32_t seed = prev ? prev[i] : 0xFFFFFFFFu;
+      if (seed != 0xFFFFFFFFu) {
+        start = (int)(seed >> 30);
+        best.pos = seed & 0x3FFFFFFFu;
+        const float4 c = __ldg(&ls.pts[start][best.pos]);
+        const float d2 = dist2_exact(c.x, c.y, c.z, s.x, s.y, s.z);
+        best.key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+        best.seeded = true;
+      }
+      if (best.seeded) {
+        // box query around the seed distance: usually one or two rows of one or two cells
+        level = start;
+        box_visit(ls.g[level], ls.cs[level], s.x, s.y, s.z, best.kth(),
+                  [&](uint32_t lo, uint32_t hi) { best.scan(ls.pts[level], lo, hi, s.x, s.y, s.z, 0); });
       } else {
-        // raw moments for Kabsch (registration.rs:157-172) and the mse (:206-218)
-        const float sv[3] = {s.x, s.y, s.z}, tv[3] = {d4.x, d4.y, d4.z};
+        level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
+      }
+      valid = best.full();
+      if (prev) prev[i] = valid ? (((uint32_t)level << 30) | best.pos) : 0xFFFFFFFFu;
+      if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
+        if (xsqrt(best.kth()) > max_dist) valid = false;
+      }
+      if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
+      if (valid) d4 = __ldg(&ls.pts[level][best.pos]);
+    }
+    float v[32];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          acc[r] += sv[r];
-          acc[3 + r] += tv[r];
+    for (int t = 0; t < 32; ++t) v[t] = 0.0f;
+    if (MODE == kPlane) {
+      float4 n4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (valid) n4 = __ldg(&tgt_nrm[__float_as_uint(d4.w)]);
+      const V3 n{n4.x, n4.y, n4.z};
+      const V3 c = xcross(s, n);  // registration.rs:418
+      const float dx = xsub(d4.x, s.x), dy = xsub(d4.y, s.y), dz = xsub(d4.z, s.z);
+      const float b = xadd(xadd(xmul(n.x, dx), xmul(n.y, dy)), xmul(n.z, dz));  // :424
+      const float a[6] = {c.x, c.y, c.z, n.x, n.y, n.z};  // all zero when there is no match
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) acc[6 + 3 * r + cc] += xmul(sv[r], tv[cc]);
-        }
-        const float dx = xsub(s.x, d4.x), dy = xsub(s.y, d4.y), dz = xsub(s.z, d4.z);
-        acc[15] += xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-        acc[16] += 1.0f;
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc) v[r * 6 - (r * (r - 1)) / 2 + (cc - r)] = xmul(a[r], a[cc]);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) v[21 + r] = xmul(a[r], b);
+      v[27] = xmul(b, b);
+      v[28] = valid ? 1.0f : 0.0f;
+    } else {
+      // raw moments for Kabsch (registration.rs:157-172) and the mse (:206-218)
+      const float m = valid ? 1.0f : 0.0f;
+      const float sv[3] = {s.x * m, s.y * m, s.z * m}, tv[3] = {d4.x, d4.y, d4.z};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        v[r] = sv[r];
+        v[3 + r] = tv[r];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) v[6 + 3 * r + cc] = xmul(sv[r], tv[cc]);
+      }
+      const float dx = xsub(sv[0], d4.x), dy = xsub(sv[1], d4.y), dz = xsub(sv[2], d4.z);
+      v[15] = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+      v[16] = m;
+    }
+    // transpose-reduce: after the step with offset o a lane holds the values whose index has the
+    // same o-bit as its lane id, summed over the lane pair; five steps leave lane j with sum j
+#pragma unroll
+    for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int t = 0; t < cnt; ++t) {
+        const float give = up ? v[t] : v[t + cnt];
+        const float keep = up ? v[t + cnt] : v[t];
+        v[t] = keep + __shfl_xor_sync(0xffffffffu, give, o);
       }
     }
+    acc += (double)v[0];
   }
-  // warp-shuffle tree, then one row per warp in shared memory
-  __shared__ double sm[kIcpBlock / 32][NS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) {
-    double v = (double)acc[i];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sm[warp][i] = v;
-  }
+  // one row per warp in shared memory
+  __shared__ double sm[kIcpBlock / 32][32];
+  sm[warp][lane] = acc;
   __syncthreads();
   if (threadIdx.x < NS) {
     double v = 0.0;
