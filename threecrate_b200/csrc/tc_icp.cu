@@ -20,6 +20,8 @@ int tci_comm_allreduce(tc_comm* comm, double* d_buf, uint64_t count);  // tc_com
 // peer exchange (tc_comm.cu): returns false when the communicator has no mapped peer buffers
 bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
                     unsigned long long* epoch_base, unsigned long long epochs_needed);
+int g_tc_icp_solve_fused = 1;  // debug: 0 = separate solve launch
+extern "C" void tc_debug_set_icp_solve_fused(int on) { g_tc_icp_solve_fused = on; }
 extern int g_tc_icp_fuse;  // 1 (default): fused tail; 0: separate all-reduce + solve launches
 
 namespace {
@@ -57,8 +59,10 @@ struct PeerXchg {
 };
 constexpr int kXSlot = 32;
 
-__device__ void icp_solve_plane(IcpState* st, const double* sums, float conv);
-__device__ void icp_solve_point(IcpState* st, const double* sums, float conv);
+// (not inlined: called once per launch by one thread of the last block; inlined into the
+//  correspondence kernel they would set its register count)
+__device__ __noinline__ void icp_solve_plane(IcpState* st, const double* sums, float conv);
+__device__ __noinline__ void icp_solve_point(IcpState* st, const double* sums, float conv);
 __device__ __forceinline__ V3 xcross(const V3& a, const V3& b) {
   return V3{xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)),
             xsub(xmul(a.x, b.y), xmul(a.y, b.x))};
@@ -110,12 +114,12 @@ k_pad_normals(const float* __restrict__ nrm, uint32_t n, float4* __restrict__ ou
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kIcpBlock)
+__global__ void __launch_bounds__(kIcpBlock, 4)  // 64 registers: the called solve may spill freely
 k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
                  const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
                  double* __restrict__ sums, uint32_t* __restrict__ match_out,
-                 uint32_t* __restrict__ prev, int fuse, PeerXchg px) {
+                 uint32_t* __restrict__ prev, int fuse, PeerXchg px, int solve_here, float conv) {
   if (st->done) return;
   float T[7];
 #pragma unroll
@@ -283,8 +287,16 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         sums[threadIdx.x] = t;
       }
     }
-    // (the 6x6 / Horn solve stays a separate one-thread launch: inlined here it would raise the
-    //  whole kernel to ~120 registers and halve the occupancy of the search)
+    // The 6x6 / Horn solve runs here too (one thread of the last block, through a real call so
+    // that its registers do not count against the search) unless an NCCL all-reduce has to
+    // happen between the sums and the solve.
+    if (solve_here) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (MODE == kPlane) icp_solve_plane(st, sums, conv);
+        else icp_solve_point(st, sums, conv);
+      }
+    }
   }
 }
 
@@ -374,7 +386,7 @@ __global__ void k_icp_solve(IcpState* __restrict__ st, const double* __restrict_
   icp_solve_plane(st, sums, conv);
 }
 
-__device__ void icp_solve_plane(IcpState* st, const double* sums, float conv) {
+__device__ __noinline__ void icp_solve_plane(IcpState* st, const double* sums, float conv) {
   const double n_valid = sums[28];
   st->n_valid = n_valid;
   if (n_valid < 6.0) {  // registration.rs:568-572
@@ -443,7 +455,7 @@ __global__ void k_icp_solve_p2p(IcpState* __restrict__ st, const double* __restr
   icp_solve_point(st, sums, conv);
 }
 
-__device__ void icp_solve_point(IcpState* st, const double* sums, float conv) {
+__device__ __noinline__ void icp_solve_point(IcpState* st, const double* sums, float conv) {
   const double n = sums[16];
   st->n_valid = n;
   if (n < 3.0) {  // registration.rs:311-315
@@ -640,17 +652,19 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
     if (comm && g_tc_icp_fuse &&
         tci_comm_peers(comm, px.peer, &px.world, &px.rank, &px.epoch_base, max_iters + 1))
       fuse = 1;
+    const int solve_here = (!comm || fuse) && g_tc_icp_solve_fused ? 1 : 0;
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
       if (mode == kPlane)
         k_icp_correspond<kPlane><<<grid, kIcpBlock, 0, ctx->stream>>>(
             ls, d_nrm, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev,
-            fuse, px);
+            fuse, px, solve_here, conv_threshold);
       else
         k_icp_correspond<kPoint><<<grid, kIcpBlock, 0, ctx->stream>>>(
             ls, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out,
-            d_prev, fuse, px);
+            d_prev, fuse, px, solve_here, conv_threshold);
       ctx->launches++;
-      if (comm && !fuse) st = tci_comm_allreduce(comm, d_sums, n_sums);
+      if (solve_here) continue;
+      st = tci_comm_allreduce(comm, d_sums, n_sums);
       if (mode == kPlane)
         k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
       else

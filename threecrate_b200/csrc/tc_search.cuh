@@ -241,13 +241,23 @@ struct Best1 {
   __device__ __forceinline__ float kth() const { return __uint_as_float((uint32_t)(key >> 32)); }
   __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
                                        float qx, float qy, float qz, int) {
-    for (uint32_t j = lo; j < hi; ++j) {
-      const float4 c = __ldg(&pts[j]);
-      const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
-      const uint64_t k2 = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
-      if (k2 < key) {
-        key = k2;
-        pos = j;
+    if (lo >= hi) return;
+    const uint32_t last = hi - 1;
+#pragma unroll 1
+    for (uint32_t base = lo; base < hi; base += 4) {
+      // four independent loads in flight (clamped: a repeated last candidate cannot win twice)
+      float4 c[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) c[t] = __ldg(&pts[min(base + t, last)]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float d2 = dist2_exact(c[t].x, c[t].y, c[t].z, qx, qy, qz);
+        const uint64_t k2 =
+            ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c[t].w);
+        if (k2 < key) {
+          key = k2;
+          pos = min(base + t, last);
+        }
       }
     }
   }
