@@ -157,13 +157,36 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         best.key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
         best.seeded = true;
       }
-      if (best.seeded) {
-        // box query around the seed distance: usually one or two rows of one or two cells
-        level = start;
-        box_visit(ls.g[level], ls.cs[level], s.x, s.y, s.z, best.kth(),
-                  [&](uint32_t lo, uint32_t hi) { best.scan(ls.pts[level], lo, hi, s.x, s.y, s.z, 0); });
-      } else {
-        level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
+      {
+        // Seeded (level << 30 | position of last iteration's match): a box query around the seed
+        // distance - one or two rows of one or two cells once the pose has settled.  Without a
+        // seed (first iteration), or when the pose jumped and the old match is cells away (second
+        // iteration of a badly aligned pair), the 2x2 rows nearest to the query are probed first:
+        // they usually hold the neighbour and shrink the box from dozens of cells to a few.
+        level = max(start, 0);
+        const GridParams& g = ls.g[level];
+        const float4* __restrict__ pts = ls.pts[level];
+        const uint32_t* __restrict__ cs = ls.cs[level];
+        auto scan = [&](uint32_t lo, uint32_t hi) { best.scan(pts, lo, hi, s.x, s.y, s.z, 0); };
+        if (!best.seeded || best.kth() > g.cell * g.cell * 0.5f) {
+          best.init();
+          float ux, uy, uz;
+          const int cx = cell_coord(s.x, g.ox, g.inv, g.nx, ux);
+          const int cy = cell_coord(s.y, g.oy, g.inv, g.ny, uy);
+          const int cz = cell_coord(s.z, g.oz, g.inv, g.nz, uz);
+          const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+          const int y2 = min(max(cy + ((uy - (float)cy < 0.5f) ? -1 : 1), 0), g.ny - 1);
+          const int z2 = min(max(cz + ((uz - (float)cz < 0.5f) ? -1 : 1), 0), g.nz - 1);
+#pragma unroll 1
+          for (int t = 0; t < 4; ++t) {
+            const int y = (t & 1) ? y2 : cy, z = (t & 2) ? z2 : cz;
+            if (((t & 1) && y2 == cy) || ((t & 2) && z2 == cz)) continue;  // clamped: same row
+            const uint32_t row = cell_id(g, 0, y, z);
+            scan(__ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]));
+          }
+        }
+        if (best.full()) box_visit(g, cs, s.x, s.y, s.z, best.kth(), scan);
+        else level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
       }
       valid = best.full();
       if (prev) prev[i] = valid ? (((uint32_t)level << 30) | best.pos) : 0xFFFFFFFFu;
