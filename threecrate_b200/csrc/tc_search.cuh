@@ -135,10 +135,14 @@ __device__ __forceinline__ void bitonic_sort_u64(uint64_t (&a)[N]) {
 // Candidates are taken L at a time; a batch holding something below the current K-th distance
 // is sorted and merged:  m[i] = min(v[i], b[L-1-i]) keeps the L smallest of the 2L and is
 // bitonic -> log2(L) merge stages.  A float compare-exchange is 2 FMNMX, branch-free.
-template <int L, bool X = false>
+template <int L, bool X = false, int B = (L < 16 ? L : 16)>
 struct SelF {
   // X adds one scalar slot `x` ranked after v[L-1] (the (L+1)-th smallest): k = 16 needs 17
   // entries, and a 16-wide network plus one min-reduction is far cheaper than the 32-wide one.
+  // B = candidates per batch (<= L).  B = 16 with L = 32 costs the same compare-exchanges per
+  // candidate as B = 32 (sort16 + merge32 per 16 vs sort32 + merge32 per 32) in half the code
+  // and with 16 fewer live registers, and the skip test below is finer grained.
+  static_assert(B <= L, "batch larger than the list");
   static constexpr int kSlots = L + (X ? 1 : 0);
   float v[L];
   float x;
@@ -150,18 +154,20 @@ struct SelF {
   }
   __device__ __forceinline__ float kth() const { return X ? x : v[L - 1]; }
   __device__ __forceinline__ bool full() const { return kth() < INFINITY; }
-  __device__ __forceinline__ void merge(float (&b)[L]) {
-    bitonic_sort_f<L>(b);
+  __device__ __forceinline__ void merge(float (&b)[B]) {
+    bitonic_sort_f<B>(b);
+    // v (ascending) vs b padded with +inf (ascending): m[i] = min(v[i], b'[L-1-i]) keeps the L
+    // smallest and is bitonic; only the top B entries of v meet a finite partner
     if (X) {
-      // the L discarded values are max(v[i], b[L-1-i]); their minimum is the (L+1)-th smallest
+      // the discarded values are max(v[L-B+i], b[B-1-i]); their minimum is the (L+1)-th smallest
       // of v u b, and every kept value is <= v[L-1] <= x, so x only competes with that minimum
       float dm = INFINITY;
 #pragma unroll
-      for (int i = 0; i < L; ++i) dm = fminf(dm, fmaxf(v[i], b[L - 1 - i]));
+      for (int i = 0; i < B; ++i) dm = fminf(dm, fmaxf(v[L - B + i], b[B - 1 - i]));
       x = fminf(x, dm);
     }
 #pragma unroll
-    for (int i = 0; i < L; ++i) v[i] = fminf(v[i], b[L - 1 - i]);
+    for (int i = 0; i < B; ++i) v[L - B + i] = fminf(v[L - B + i], b[B - 1 - i]);
     bitonic_merge_f<L>(v);
   }
   // number of list entries strictly below d2 (sentinels included)
@@ -186,11 +192,11 @@ struct SelF {
     if (lo >= hi) return;
     const uint32_t last = hi - 1;
 #pragma unroll 1
-    for (uint32_t base = lo; base < hi; base += L) {
-      float b[L];
+    for (uint32_t base = lo; base < hi; base += B) {
+      float b[B];
       float bm = INFINITY;
 #pragma unroll
-      for (int t = 0; t < L; ++t) {
+      for (int t = 0; t < B; ++t) {
         // unconditional load from a clamped index: the loads of a batch are independent and
         // can all be in flight together; out-of-range slots are masked to +inf afterwards
         const uint32_t j = min(base + t, last);
