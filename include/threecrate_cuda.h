@@ -70,6 +70,35 @@ int tc_cloud_upload_strided(tc_context* ctx, const void* base, uint64_t n, uint3
 int tc_cloud_from_device(tc_context* ctx, const float* d_xyz_aos, uint64_t n, tc_cloud** out);
 void tc_cloud_free(tc_cloud* cloud);
 uint64_t tc_cloud_len(const tc_cloud* cloud);
+/* Copy the points back to host AoS f32 (n x 3); synchronises the context's stream. */
+int tc_cloud_download(tc_context* ctx, const tc_cloud* cloud, float* xyz_aos_out);
+
+/* ---- filters (threecrate-algorithms/src/filtering.rs) -------------------------------------
+ * Each returns a NEW device-resident cloud in *out (free with tc_cloud_free); an empty input
+ * yields an empty cloud, as in the reference.
+ * voxel_grid_filter (filtering.rs:38-133): one centroid per occupied voxel, voxel =
+ * floor((p - bbox_min) / voxel_size) per axis, centroid summed in f64 in original point order and
+ * rounded to f32 like the reference.  Output order: ascending (z, y, x) voxel coordinate (the
+ * reference's order is a HashMap iteration order).  voxel_size <= 0 -> TC_INVALID_DATA. */
+int tc_voxel_grid_filter(tc_context* ctx, const tc_cloud* cloud, float voxel_size, tc_cloud** out);
+/* radius_outlier_removal (filtering.rs:167-218): keeps, in original order, the points with at
+ * least `min_neighbors` OTHER points within `radius` (d2 <= radius^2).  radius <= 0 or
+ * min_neighbors == 0 -> TC_INVALID_DATA. */
+int tc_radius_outlier_removal(tc_context* ctx, const tc_cloud* cloud, float radius,
+                              uint32_t min_neighbors, tc_cloud** out);
+/* statistical_outlier_removal (filtering.rs:253-321) and .._with_threshold (:335-394): keeps, in
+ * original order, the points whose mean distance to their k nearest neighbours (kNN(k+1), every
+ * neighbour with the point's own coordinates skipped, f32 sum in ascending-distance order) is
+ * <= threshold.
+ *   mode 0: threshold = mean + value * std_dev of those mean distances, accumulated like the
+ *           reference (sequential f32 sums over the cloud) - bit-exact, ~2 ns/point serial tail;
+ *   mode 1: same statistics from f64 tree sums (fast; a point whose mean distance lies within the
+ *           reference's own f32 accumulation error of the threshold may be classified differently);
+ *   mode 2: `value` IS the threshold (statistical_outlier_removal_with_threshold).
+ * stats_out (may be NULL) receives {global mean, std dev, threshold}.  k_neighbors == 0 or
+ * value <= 0 -> TC_INVALID_DATA; k_neighbors > 63 is not supported by the device top-k. */
+int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* cloud, uint32_t k_neighbors,
+                                   float value, int mode, float* stats_out, tc_cloud** out);
 
 /* ---- spatial index (replaces KdTree::new, nearest_neighbor.rs:37-60) ---------------------- */
 /* Builds the uniform grid: bbox -> cell keys -> hand-written LSD radix sort -> cell-range scan ->
@@ -175,6 +204,25 @@ int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud*
                                  const tc_index* tgt_index, const float init[7], uint32_t max_iters,
                                  float max_corr_dist, float conv_threshold, tc_icp_result* out,
                                  uint32_t* d_match_out);
+
+/* multiscale_icp_point_to_point (registration.rs:704-789): coarse-to-fine point-to-point ICP.
+ * Per level both clouds are voxel-downsampled (tc_voxel_grid_filter) and icp_point_to_point runs
+ * from the previous level's transform (levels whose downsampled clouds hold < 3 points are
+ * skipped); a final refinement runs on the full clouds.  iterations = sum over all stages;
+ * pairs_out (may be NULL, 2 x ns u64) = the final stage's correspondences.
+ * max_correspondence_distance < 0 means None. */
+typedef struct tc_icp_scale_level {
+  float voxel_size;
+  uint32_t max_iterations;
+  float max_correspondence_distance;
+} tc_icp_scale_level;
+int tc_multiscale_icp_point_to_point(tc_context* ctx, const float* src_aos, uint64_t ns,
+                                     const float* tgt_aos, uint64_t nt, const float init[7],
+                                     const tc_icp_scale_level* levels, uint32_t n_levels,
+                                     uint32_t final_refinement_iterations,
+                                     float final_max_correspondence_distance,
+                                     float convergence_threshold, tc_icp_result* out,
+                                     uint64_t* pairs_out);
 
 /* ---- multi-GPU (one process per GPU; NCCL bootstrap, id exchanged out of band) ------------- */
 #define TC_COMM_ID_BYTES 128

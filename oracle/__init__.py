@@ -9,8 +9,19 @@ PARITY UNPINNED: the reference is Rust-only (no toolchain here) and holds no gol
 for this path; the oracle is pinned by the reference's own inline test assertions and by
 independent numpy/scipy cross-checks (tests/test_oracle_*.py).
 """
+from .filters import (  # noqa: F401
+    multiscale_icp_point_to_point,
+    radius_outlier_removal,
+    sor_mean_distances,
+    sor_threshold,
+    statistical_outlier_removal,
+    statistical_outlier_removal_with_threshold,
+    voxel_grid_filter,
+)
 from .oracle import (  # noqa: F401
+    AlgorithmError,
     IcpResult,
+    InvalidData,
     OracleKdTree,
     brute_knn,
     build,

@@ -19,6 +19,8 @@ from .api import (  # noqa: F401
     GridIndex,
     ICPResult,
     IDENTITY,
+    IcpScaleLevel,
+    MultiScaleIcpConfig,
     InvalidData,
     KdTree,
     NormalEstimationConfig,
@@ -35,7 +37,12 @@ from .api import (  # noqa: F401
     icp_point_to_plane_device,
     icp_point_to_point_device,
     k_nearest_neighbors,
+    multiscale_icp_point_to_point,
     pinned_empty,
+    radius_outlier_removal,
+    statistical_outlier_removal,
+    statistical_outlier_removal_with_threshold,
+    voxel_grid_filter,
 )
 
 __version__ = "0.1.0"

@@ -51,6 +51,11 @@ _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
 
 # every symbol include/threecrate_cuda.h declares: name -> (restype, argtypes)
+class IcpScaleLevelC(C.Structure):
+    _fields_ = [("voxel_size", C.c_float), ("max_iterations", C.c_uint32),
+                ("max_correspondence_distance", C.c_float)]
+
+
 SYMBOLS = {
     "tc_context_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "tc_context_destroy": (None, [_vp]),
@@ -66,6 +71,11 @@ SYMBOLS = {
     "tc_cloud_from_device": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "tc_cloud_free": (None, [_vp]),
     "tc_cloud_len": (C.c_uint64, [_vp]),
+    "tc_cloud_download": (C.c_int, [_vp, _vp, _vp]),
+    "tc_voxel_grid_filter": (C.c_int, [_vp, _vp, C.c_float, C.POINTER(_vp)]),
+    "tc_radius_outlier_removal": (C.c_int, [_vp, _vp, C.c_float, C.c_uint32, C.POINTER(_vp)]),
+    "tc_statistical_outlier_removal": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, C.c_int, _vp,
+                                                 C.POINTER(_vp)]),
     "tc_index_build": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, C.POINTER(_vp)]),
     "tc_index_free": (None, [_vp]),
     "tc_index_get_info": (C.c_int, [_vp, C.POINTER(IndexInfoC)]),
@@ -84,6 +94,10 @@ SYMBOLS = {
                                         C.c_float, C.c_float, C.POINTER(IcpResultC), _vp]),
     "tc_icp_point_to_point_device": (C.c_int, [_vp, _vp, _vp, _vp, _f32p, C.c_uint32, C.c_float,
                                                C.c_float, C.POINTER(IcpResultC), _vp]),
+    "tc_multiscale_icp_point_to_point": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _f32p,
+                                                   C.POINTER(IcpScaleLevelC), C.c_uint32,
+                                                   C.c_uint32, C.c_float, C.c_float,
+                                                   C.POINTER(IcpResultC), _vp]),
     "tc_comm_get_unique_id": (C.c_int, [_vp, _vp]),
     "tc_comm_init_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "tc_comm_destroy": (None, [_vp]),

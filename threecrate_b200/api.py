@@ -144,8 +144,21 @@ class DeviceCloud:
         self.ctx.check(st)
         self.h = h
 
+    @classmethod
+    def _from_handle(cls, ctx: "Context", h) -> "DeviceCloud":
+        c = cls.__new__(cls)
+        c.ctx, c.h = ctx, h
+        c.n = int(ctx.lib.tc_cloud_len(h))
+        return c
+
     def __len__(self):
         return self.n
+
+    def download(self) -> np.ndarray:
+        """The points as a host (n, 3) float32 array (tc_cloud_download)."""
+        out = np.empty((self.n, 3), np.float32)
+        self.ctx.check(self.ctx.lib.tc_cloud_download(self.ctx.h, self.h, _vp(out.ctypes.data)))
+        return out
 
     def free(self):
         if getattr(self, "h", None):
@@ -433,6 +446,141 @@ def icp(source, target, init=IDENTITY, max_iters: int = 50, ctx: Optional[Contex
                             want_correspondences=False).transformation
     except ThreecrateError:
         return np.ascontiguousarray(init, np.float32).reshape(7)
+
+
+# --------------------------------------------------------------------------------------------
+# filters (threecrate-algorithms/src/filtering.rs) — host arrays or DeviceCloud in, same kind out
+# --------------------------------------------------------------------------------------------
+def _as_cloud(points, ctx: Optional[Context]):
+    if isinstance(points, DeviceCloud):
+        return points, False
+    return DeviceCloud(_pts(points), ctx), True
+
+
+def _filter_result(ctx: Context, h, owned_input: Optional[DeviceCloud], host: bool):
+    out = DeviceCloud._from_handle(ctx, h)
+    if owned_input is not None:
+        owned_input.free()
+    if not host:
+        return out
+    pts = out.download()
+    out.free()
+    return pts
+
+
+def voxel_grid_filter(points, voxel_size: float, ctx: Optional[Context] = None):
+    """filtering.rs:38-133: one centroid per occupied voxel (ascending (z, y, x) voxel order)."""
+    cloud, owned = _as_cloud(points, ctx)
+    h = _vp()
+    try:
+        cloud.ctx.check(cloud.ctx.lib.tc_voxel_grid_filter(cloud.ctx.h, cloud.h, float(voxel_size),
+                                                          C.byref(h)))
+    except ThreecrateError:
+        if owned:
+            cloud.free()
+        raise
+    return _filter_result(cloud.ctx, h, cloud if owned else None, owned)
+
+
+def radius_outlier_removal(points, radius: float, min_neighbors: int,
+                           ctx: Optional[Context] = None):
+    """filtering.rs:167-218: keep points with >= min_neighbors other points within radius."""
+    if min_neighbors < 0:
+        raise InvalidData("min_neighbors must be greater than 0")
+    cloud, owned = _as_cloud(points, ctx)
+    h = _vp()
+    try:
+        cloud.ctx.check(cloud.ctx.lib.tc_radius_outlier_removal(
+            cloud.ctx.h, cloud.h, float(radius), int(min_neighbors), C.byref(h)))
+    except ThreecrateError:
+        if owned:
+            cloud.free()
+        raise
+    return _filter_result(cloud.ctx, h, cloud if owned else None, owned)
+
+
+def _sor(points, k_neighbors: int, value: float, mode: int, ctx, return_stats: bool):
+    if k_neighbors < 0:
+        raise InvalidData("k_neighbors must be greater than 0")
+    cloud, owned = _as_cloud(points, ctx)
+    h = _vp()
+    stats = (C.c_float * 3)()
+    try:
+        cloud.ctx.check(cloud.ctx.lib.tc_statistical_outlier_removal(
+            cloud.ctx.h, cloud.h, int(k_neighbors), float(value), int(mode), stats, C.byref(h)))
+    except ThreecrateError:
+        if owned:
+            cloud.free()
+        raise
+    res = _filter_result(cloud.ctx, h, cloud if owned else None, owned)
+    if return_stats:
+        return res, {"mean": stats[0], "std_dev": stats[1], "threshold": stats[2]}
+    return res
+
+
+def statistical_outlier_removal(points, k_neighbors: int, std_dev_multiplier: float,
+                                ctx: Optional[Context] = None, fast: bool = False,
+                                return_stats: bool = False):
+    """filtering.rs:253-321.  fast=False accumulates the global mean / variance like the
+    reference (sequential f32, bit-exact); fast=True uses f64 tree sums."""
+    return _sor(points, k_neighbors, std_dev_multiplier, 1 if fast else 0, ctx, return_stats)
+
+
+def statistical_outlier_removal_with_threshold(points, k_neighbors: int, threshold: float,
+                                               ctx: Optional[Context] = None):
+    """filtering.rs:335-394"""
+    return _sor(points, k_neighbors, threshold, 2, ctx, False)
+
+
+# --------------------------------------------------------------------------------------------
+# multiscale point-to-point ICP (registration.rs:26-71, 704-789)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class IcpScaleLevel:
+    voxel_size: float
+    max_iterations: int
+    max_correspondence_distance: Optional[float] = None
+
+
+@dataclass
+class MultiScaleIcpConfig:
+    """Defaults of registration.rs:46-71."""
+    levels: list = field(default_factory=lambda: [IcpScaleLevel(0.20, 10, 0.50),
+                                                  IcpScaleLevel(0.10, 10, 0.25),
+                                                  IcpScaleLevel(0.05, 15, 0.15)])
+    final_refinement_iterations: int = 10
+    final_max_correspondence_distance: Optional[float] = 0.10
+    convergence_threshold: float = 1e-5
+
+
+def multiscale_icp_point_to_point(source, target, init=IDENTITY,
+                                  config: Optional[MultiScaleIcpConfig] = None,
+                                  ctx: Optional[Context] = None,
+                                  want_correspondences: bool = True) -> ICPResult:
+    """registration.rs:704-789"""
+    config = config or MultiScaleIcpConfig()
+    src, tgt = _pts(source, "source"), _pts(target, "target")
+    init7 = np.ascontiguousarray(init, np.float32).reshape(7)
+    ctx = ctx or default_context()
+    nl = len(config.levels)
+    levels = (_lib.IcpScaleLevelC * max(nl, 1))()
+    for i, lv in enumerate(config.levels):
+        levels[i].voxel_size = float(lv.voxel_size)
+        levels[i].max_iterations = int(lv.max_iterations)
+        levels[i].max_correspondence_distance = (
+            -1.0 if lv.max_correspondence_distance is None else float(lv.max_correspondence_distance))
+    res = _lib.IcpResultC()
+    pairs = np.zeros((max(src.shape[0], 1), 2), np.uint64) if want_correspondences else None
+    fm = config.final_max_correspondence_distance
+    ctx.check(ctx.lib.tc_multiscale_icp_point_to_point(
+        ctx.h, _vp(src.ctypes.data), src.shape[0], _vp(tgt.ctypes.data), tgt.shape[0],
+        init7.ctypes.data_as(C.POINTER(C.c_float)), levels, nl,
+        int(config.final_refinement_iterations), -1.0 if fm is None else float(fm),
+        float(config.convergence_threshold), C.byref(res),
+        None if pairs is None else _vp(pairs.ctypes.data)))
+    corr = pairs[: res.n_correspondences].copy() if pairs is not None else np.empty((0, 2), np.uint64)
+    return ICPResult(np.array(res.transform[:], np.float32), float(res.mse), int(res.iterations),
+                     bool(res.converged), corr)
 
 
 # --------------------------------------------------------------------------------------------

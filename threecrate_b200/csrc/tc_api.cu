@@ -233,6 +233,16 @@ extern "C" int tc_cloud_from_device(tc_context* ctx, const float* d_xyz_aos, uin
   return TC_OK;
 }
 
+extern "C" int tc_cloud_download(tc_context* ctx, const tc_cloud* cloud, float* xyz_aos_out) {
+  TC_ENTER(ctx);
+  if (!cloud || (cloud->n > 0 && !xyz_aos_out)) return TC_INVALID_DATA;
+  if (cloud->n > 0)
+    TC_CUDA(ctx, cudaMemcpyAsync(xyz_aos_out, cloud->d_xyz, 3 * cloud->n * sizeof(float),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TC_OK;
+}
+
 extern "C" void tc_cloud_free(tc_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
@@ -511,22 +521,15 @@ extern "C" int tc_icp_point_to_plane(tc_context* ctx, const float* src_aos, uint
   return st;
 }
 
-extern "C" int tc_icp_point_to_point(tc_context* ctx, const float* src_aos, uint64_t ns,
-                                     const float* tgt_aos, uint64_t nt, const float init[7],
-                                     uint32_t max_iters, float max_corr_dist, float conv_threshold,
-                                     tc_icp_result* out, uint64_t* pairs_out) {
-  TC_ENTER(ctx);
-  // validation order of registration.rs:266-276
-  if (ns == 0 || nt == 0)
-    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
-  if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
-  if (!src_aos || !tgt_aos || !init || !out) return TC_INVALID_DATA;
-  tc_cloud *src = nullptr, *tgt = nullptr;
+// icp_detailed on device-resident clouds: KdTree::new(target) (registration.rs:281), the device
+// loop, and optionally the (source index, target index) pairs of the final iteration
+static int p2p_on_clouds(tc_context* ctx, const tc_cloud* src, const tc_cloud* tgt,
+                         const float init[7], uint32_t max_iters, float max_corr_dist,
+                         float conv_threshold, tc_icp_result* out, uint64_t* pairs_out) {
+  const uint64_t ns = src->n;
   tc_index* ix = nullptr;
   uint32_t* d_match = nullptr;
-  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
-  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
-  if (st == TC_OK) st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);  // KdTree::new(target), :281
+  int st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);
   if (st == TC_OK && pairs_out) st = tc_alloc(ctx, &d_match, ns);
   if (st == TC_OK)
     st = tc_icp_point_to_point_device(ctx, nullptr, src, ix, init, max_iters, max_corr_dist,
@@ -551,6 +554,88 @@ extern "C" int tc_icp_point_to_point(tc_context* ctx, const float* src_aos, uint
   }
   tc_free(ctx, d_match);
   tc_index_free(ix);
+  return st;
+}
+
+extern "C" int tc_icp_point_to_point(tc_context* ctx, const float* src_aos, uint64_t ns,
+                                     const float* tgt_aos, uint64_t nt, const float init[7],
+                                     uint32_t max_iters, float max_corr_dist, float conv_threshold,
+                                     tc_icp_result* out, uint64_t* pairs_out) {
+  TC_ENTER(ctx);
+  // validation order of registration.rs:266-276
+  if (ns == 0 || nt == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
+  if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
+  if (!src_aos || !tgt_aos || !init || !out) return TC_INVALID_DATA;
+  tc_cloud *src = nullptr, *tgt = nullptr;
+  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
+  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
+  if (st == TC_OK)
+    st = p2p_on_clouds(ctx, src, tgt, init, max_iters, max_corr_dist, conv_threshold, out,
+                       pairs_out);
+  tc_cloud_free(tgt);
+  tc_cloud_free(src);
+  return st;
+}
+
+// multiscale_icp_point_to_point (registration.rs:704-789): per level, voxel-downsample both
+// clouds and run icp_point_to_point from the previous level's transform; then refine on the
+// full clouds.  Everything between the two uploads and the final read-back stays on the device.
+extern "C" int tc_multiscale_icp_point_to_point(
+    tc_context* ctx, const float* src_aos, uint64_t ns, const float* tgt_aos, uint64_t nt,
+    const float init[7], const tc_icp_scale_level* levels, uint32_t n_levels,
+    uint32_t final_refinement_iterations, float final_max_corr_dist, float conv_threshold,
+    tc_icp_result* out, uint64_t* pairs_out) {
+  TC_ENTER(ctx);
+  // validation order of registration.rs:710-734
+  if (ns == 0 || nt == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
+  if (n_levels == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "At least one ICP scale level is required");
+  if (conv_threshold <= 0.0f)
+    return tc_fail(ctx, TC_INVALID_DATA, "Convergence threshold must be positive");
+  if (final_refinement_iterations == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "Final refinement iterations must be positive");
+  if (!src_aos || !tgt_aos || !init || !levels || !out) return TC_INVALID_DATA;
+  tc_cloud *src = nullptr, *tgt = nullptr;
+  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
+  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
+  float T[7];
+  for (int i = 0; i < 7; ++i) T[i] = init[i];
+  uint32_t total_iterations = 0;
+  bool any = false;
+  for (uint32_t l = 0; l < n_levels && st == TC_OK; ++l) {
+    const tc_icp_scale_level& lv = levels[l];
+    if (lv.voxel_size <= 0.0f) {
+      st = tc_fail(ctx, TC_INVALID_DATA, "Scale voxel_size must be positive");
+      break;
+    }
+    if (lv.max_iterations == 0) {
+      st = tc_fail(ctx, TC_INVALID_DATA, "Scale max_iterations must be positive");
+      break;
+    }
+    tc_cloud *sd = nullptr, *td = nullptr;
+    st = tc_voxel_grid_filter(ctx, src, lv.voxel_size, &sd);
+    if (st == TC_OK) st = tc_voxel_grid_filter(ctx, tgt, lv.voxel_size, &td);
+    if (st == TC_OK && sd->n >= 3 && td->n >= 3) {
+      tc_icp_result r{};
+      st = p2p_on_clouds(ctx, sd, td, T, lv.max_iterations, lv.max_correspondence_distance,
+                         conv_threshold, &r, nullptr);
+      if (st == TC_OK) {
+        for (int i = 0; i < 7; ++i) T[i] = r.transform[i];
+        total_iterations += r.iterations;
+        any = true;
+      }
+    }
+    tc_cloud_free(sd);
+    tc_cloud_free(td);
+  }
+  if (st == TC_OK && !any)
+    st = tc_fail(ctx, TC_ALGORITHM, "No multiscale ICP level had enough downsampled points");
+  if (st == TC_OK)
+    st = p2p_on_clouds(ctx, src, tgt, T, final_refinement_iterations, final_max_corr_dist,
+                       conv_threshold, out, pairs_out);
+  if (st == TC_OK) out->iterations += total_iterations;
   tc_cloud_free(tgt);
   tc_cloud_free(src);
   return st;

@@ -480,14 +480,15 @@ int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_ou
 }
 
 int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_alt,
-                         uint32_t* d_vals_alt, uint32_t n, int key_bits, uint32_t** keys_out,
-                         uint32_t** vals_out) {
-  // d_vals may be nullptr on entry => identity values; the result then lands in the alt buffers
-  // or (d_keys, d_vals_alt2) — to keep it simple the caller always provides both value buffers.
+                         uint32_t* d_vals_alt, uint32_t n, int key_bits, bool vals_given,
+                         uint32_t** keys_out, uint32_t** vals_out) {
+  // Stable.  Values start as the identity permutation unless `vals_given` (then d_vals holds
+  // them); the caller always provides both value buffers, the result lands in one of each pair.
   const uint32_t n_tiles = (n + kRsTile - 1) / kRsTile;
   uint32_t* d_hist = nullptr;
   TC_TRY(tc_alloc(ctx, &d_hist, (uint64_t)256 * n_tiles + 1));
-  uint32_t *kin = d_keys, *kout = d_keys_alt, *vin = nullptr, *vout = d_vals_alt;
+  uint32_t *kin = d_keys, *kout = d_keys_alt, *vin = vals_given ? d_vals : nullptr,
+           *vout = d_vals_alt;
   uint32_t* vother = d_vals;
   const int passes = (key_bits + 7) / 8;
   for (int p = 0; p < passes; ++p) {
@@ -853,7 +854,7 @@ int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const Grid
     ctx->launches++;
     const uint64_t n_cells = (uint64_t)g.nx * g.ny * g.nz;
     st = tci_radix_sort_pairs(ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n,
-                              key_bits_for(n_cells), &ks, &vs);
+                              key_bits_for(n_cells), false, &ks, &vs);
   }
   if (st == TC_OK) st = tc_alloc(ctx, d_sorted, n);
   if (st == TC_OK) {

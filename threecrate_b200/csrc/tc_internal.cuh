@@ -133,8 +133,8 @@ int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float
 int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const GridParams& g,
                      float4** d_sorted);
 int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_alt,
-                         uint32_t* d_vals_alt, uint32_t n, int key_bits, uint32_t** keys_out,
-                         uint32_t** vals_out);
+                         uint32_t* d_vals_alt, uint32_t n, int key_bits, bool vals_given,
+                         uint32_t** keys_out, uint32_t** vals_out);
 int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 
 // tc_search.cu
