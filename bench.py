@@ -268,10 +268,10 @@ def main():
 
     kern_s = float(np.mean(ms_kernel)) * 1e-3
     achieved = BYTES_NORMALS_PER_PT * n / kern_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_normals2<32> (fused two-pass kNN + covariance + eigen + orientation; incl. the tie-list launch)",
+    roofline = {"bound": "hbm", "kernel": "k_normals2<16,+1> (fused two-pass kNN + covariance + eigen + orientation; incl. the tie-list launch)",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "peak_kind": f"of {peak_kind}", "traffic": 4.85e6,
-                "traffic_source": "profiles/r01b_c2_normals_raw.csv (ncu --set full, dram read+write per launch)",
+                "peak_kind": f"of {peak_kind}", "traffic": 5.61e6,
+                "traffic_source": "profiles/r01c_c2_raw.csv (ncu --set full, dram read+write per launch)",
                 "algorithmic_bytes_per_launch": BYTES_NORMALS_PER_PT * n,
                 "kernel_ms": 1e3 * kern_s, "index_build_ms": float(np.mean(ms_index)),
                 "note": "C2 (1.4 MB) is L2-resident and issue-bound, not HBM-bound; see DESIGN.md"}
@@ -375,7 +375,8 @@ def bench_c4(args, tc, synth, ctx, ext, rank, world, barrier, max_over_ranks, pe
         "points_per_s_kernel_only": n / (ms_kernel_max * 1e-3), "ms_index_build": ms_index,
         "ms_normals_kernel": ms_kernel_max, "scaling": "strong (queries sharded, grid replicated)",
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": ach / peak_gbs, "kernel": "k_normals2<32>"},
+                     "frac": ach / peak_gbs, "kernel": "k_normals2<32> (16-candidate batches)",
+                     "traffic": 1.124e9, "traffic_source": "profiles/r01c_c4_raw.csv"},
         "index_build_roofline": {"achieved": ach_build, "peak": peak_gbs, "unit": "GB/s",
                                  "frac": ach_build / peak_gbs, "bytes_per_point": BYTES_INDEX_PER_PT},
         "grid": {"cell_size": info["cell_size"], "dims": info["dims"],
