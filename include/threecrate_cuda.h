@@ -205,6 +205,18 @@ int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud*
                                  float max_corr_dist, float conv_threshold, tc_icp_result* out,
                                  uint32_t* d_match_out);
 
+/* gicp (threecrate-algorithms/src/gicp.rs:117-312), GicpConfig as plain arguments (defaults:
+ * 50 iterations, max distance 1.0, convergence 1e-6, k_correspondences 20).  Per-point
+ * covariances from kNN(max(k,4)) including the point itself (+1e-4 I), correspondences by exact
+ * 1-NN within max_correspondence_distance, Gauss-Newton on M = C_t + R C_s R^T with the 6x6
+ * system reduced in f64 on the device.  Errors as in the reference: empty cloud, zero
+ * iterations, fewer points than max(k,4), coplanar/collinear cloud (bbox extent < 1e-4) ->
+ * TC_INVALID_DATA; fewer than 6 correspondences or a singular system -> TC_ALGORITHM. */
+int tc_gicp(tc_context* ctx, const float* src_aos, uint64_t ns, const float* tgt_aos, uint64_t nt,
+            const float init[7], uint32_t max_iterations, float max_correspondence_distance,
+            float convergence_threshold, uint32_t k_correspondences, tc_icp_result* out,
+            uint64_t* pairs_out);
+
 /* multiscale_icp_point_to_point (registration.rs:704-789): coarse-to-fine point-to-point ICP.
  * Per level both clouds are voxel-downsampled (tc_voxel_grid_filter) and icp_point_to_point runs
  * from the previous level's transform (levels whose downsampled clouds hold < 3 points are

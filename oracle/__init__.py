@@ -26,6 +26,8 @@ from .oracle import (  # noqa: F401
     brute_knn,
     build,
     estimate_normals,
+    gicp,
+    gicp_covariances,
     icp_point_to_plane,
     icp_point_to_point,
     iso_apply,

@@ -1406,3 +1406,304 @@ int orc_solve6(const float* ata36_rowmajor, const float* atb6, float* x6) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// GICP (threecrate-algorithms/src/gicp.rs).  nalgebra pieces restated [upstream, not under
+// /root/reference]: Matrix3 products accumulate sum_k a(i,k) b(k,j) in k order; Matrix3::
+// try_inverse is the adjugate / determinant formula with a zero-determinant test;
+// UnitQuaternion::to_rotation_matrix is the usual ww+ii-jj-kk form.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct M3 {
+  float m[3][3];
+};
+inline M3 m3_mul(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i][j] = (a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j]) + a.m[i][2] * b.m[2][j];
+  return r;
+}
+inline M3 m3_t(const M3& a) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+  return r;
+}
+inline V3 m3_vec(const M3& a, const V3& v) {
+  return V3{(a.m[0][0] * v.x + a.m[0][1] * v.y) + a.m[0][2] * v.z,
+            (a.m[1][0] * v.x + a.m[1][1] * v.y) + a.m[1][2] * v.z,
+            (a.m[2][0] * v.x + a.m[2][1] * v.y) + a.m[2][2] * v.z};
+}
+inline bool m3_try_inverse(const M3& a, M3& out) {
+  const float m11 = a.m[0][0], m12 = a.m[0][1], m13 = a.m[0][2];
+  const float m21 = a.m[1][0], m22 = a.m[1][1], m23 = a.m[1][2];
+  const float m31 = a.m[2][0], m32 = a.m[2][1], m33 = a.m[2][2];
+  const float minor_m12_m23 = m22 * m33 - m32 * m23;
+  const float minor_m11_m23 = m21 * m33 - m31 * m23;
+  const float minor_m11_m22 = m21 * m32 - m31 * m22;
+  const float det = (m11 * minor_m12_m23 - m12 * minor_m11_m23) + m13 * minor_m11_m22;
+  if (det == 0.0f) return false;
+  out.m[0][0] = minor_m12_m23 / det;
+  out.m[0][1] = (m13 * m32 - m33 * m12) / det;
+  out.m[0][2] = (m12 * m23 - m22 * m13) / det;
+  out.m[1][0] = -minor_m11_m23 / det;
+  out.m[1][1] = (m11 * m33 - m31 * m13) / det;
+  out.m[1][2] = (m13 * m21 - m23 * m11) / det;
+  out.m[2][0] = minor_m11_m22 / det;
+  out.m[2][1] = (m12 * m31 - m32 * m11) / det;
+  out.m[2][2] = (m11 * m22 - m21 * m12) / det;
+  return true;
+}
+inline M3 quat_to_matrix(const Quat& q) {
+  const float i = q.i, j = q.j, k = q.k, w = q.w;
+  const float ww = w * w, ii = i * i, jj = j * j, kk = k * k;
+  const float ij = i * j * 2.0f, wk = w * k * 2.0f, wj = w * j * 2.0f, ik = i * k * 2.0f,
+              jk = j * k * 2.0f, wi = w * i * 2.0f;
+  M3 r;
+  r.m[0][0] = ww + ii - jj - kk;
+  r.m[0][1] = ij - wk;
+  r.m[0][2] = wj + ik;
+  r.m[1][0] = wk + ij;
+  r.m[1][1] = ww - ii + jj - kk;
+  r.m[1][2] = jk - wi;
+  r.m[2][0] = ik - wj;
+  r.m[2][1] = wi + jk;
+  r.m[2][2] = ww - ii - jj + kk;
+  return r;
+}
+// -skew_sym(v)  (gicp.rs:50-53, 222)
+inline M3 neg_skew(const V3& v) {
+  M3 r;
+  r.m[0][0] = -0.0f;
+  r.m[0][1] = v.z;
+  r.m[0][2] = -v.y;
+  r.m[1][0] = -v.z;
+  r.m[1][1] = -0.0f;
+  r.m[1][2] = v.x;
+  r.m[2][0] = v.y;
+  r.m[2][1] = -v.x;
+  r.m[2][2] = -0.0f;
+  return r;
+}
+
+// compute_covariances (gicp.rs:58-95): kNN(k) INCLUDING the point itself, mean by fold, outer
+// products accumulated in neighbour order, / max(n-1, 1), + 1e-4 I
+void gicp_covariances(const float* xyz, uint64_t n, uint64_t k, std::vector<M3>& covs, int nth) {
+  k = std::max<uint64_t>(k, 4);
+  KdTree* tree = kd_new(xyz, n);
+  covs.resize(n);
+#pragma omp parallel num_threads(nth)
+  {
+    std::vector<Neighbor> out;
+    std::vector<uint32_t> stack;
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      kd_find_k_nearest(*tree, P3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, k, out, stack);
+      M3 c;
+      std::memset(&c, 0, sizeof(c));
+      const size_t m = out.size();
+      if (m < 3) {
+        c.m[0][0] = c.m[1][1] = c.m[2][2] = 1.0f * 1e-3f;
+        covs[i] = c;
+        continue;
+      }
+      const float nf = (float)m;
+      float mx = 0.0f, my = 0.0f, mz = 0.0f;
+      for (const Neighbor& nb : out) {
+        mx += xyz[3 * nb.index];
+        my += xyz[3 * nb.index + 1];
+        mz += xyz[3 * nb.index + 2];
+      }
+      mx /= nf;
+      my /= nf;
+      mz /= nf;
+      for (const Neighbor& nb : out) {
+        const float d[3] = {xyz[3 * nb.index] - mx, xyz[3 * nb.index + 1] - my,
+                            xyz[3 * nb.index + 2] - mz};
+        for (int r = 0; r < 3; ++r)
+          for (int cc = 0; cc < 3; ++cc) c.m[r][cc] += d[r] * d[cc];
+      }
+      const float den = std::max(nf - 1.0f, 1.0f);
+      for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) c.m[r][cc] /= den;
+      for (int r = 0; r < 3; ++r) c.m[r][r] += 1.0f * 1e-4f;
+      covs[i] = c;
+    }
+  }
+  delete tree;
+}
+}  // namespace
+
+extern "C" {
+// gicp (gicp.rs:117-312).  Returns 0 OK, 1 InvalidData (detail in *why: 1 empty, 2 max_iters,
+// 3 too few points, 4 coplanar source, 5 coplanar target), 2 insufficient correspondences,
+// 3 ill-conditioned.
+int orc_gicp(const float* src, uint64_t ns, const float* tgt, uint64_t nt, const float* init7,
+             uint64_t max_iters, float max_dist, float conv, uint64_t k_corr, orc_icp_result* res,
+             uint64_t* pairs_out, int* why, int threads) {
+  *why = 0;
+  if (ns == 0 || nt == 0) {
+    *why = 1;
+    return 1;
+  }
+  if (max_iters == 0) {
+    *why = 2;
+    return 1;
+  }
+  const uint64_t min_k = std::max<uint64_t>(k_corr, 4);
+  if (ns < min_k || nt < min_k) {
+    *why = 3;
+    return 1;
+  }
+  for (int which = 0; which < 2; ++which) {  // gicp.rs:148-166
+    const float* p = which == 0 ? src : tgt;
+    const uint64_t n = which == 0 ? ns : nt;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint64_t i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = std::fmin(mn[a], p[3 * i + a]);
+        mx[a] = std::fmax(mx[a], p[3 * i + a]);
+      }
+    float min_extent = INFINITY;
+    for (int a = 0; a < 3; ++a) min_extent = std::fmin(min_extent, mx[a] - mn[a]);
+    if (min_extent < 1e-4f) {
+      *why = 4 + which;
+      return 1;
+    }
+  }
+  const int nth = threads > 0 ? threads : orc_max_threads();
+  std::vector<M3> scov, tcov;
+  gicp_covariances(src, ns, k_corr, scov, nth);
+  gicp_covariances(tgt, nt, k_corr, tcov, nth);
+  KdTree* tree = kd_new(tgt, nt);
+  Iso T{Quat{init7[3], init7[4], init7[5], init7[6]}, V3{init7[0], init7[1], init7[2]}};
+  float prev_mse = INFINITY;
+  std::vector<std::pair<uint64_t, uint64_t>> final_corr, corr_pairs;
+  std::vector<V3> ts(ns);
+  std::vector<int64_t> corr_idx(ns);
+  std::vector<float> corr_dist(ns);
+  auto finish = [&](float mse, uint64_t iters, int converged,
+                    const std::vector<std::pair<uint64_t, uint64_t>>& pairs) {
+    res->t[0] = T.t.x;
+    res->t[1] = T.t.y;
+    res->t[2] = T.t.z;
+    res->q[0] = T.q.i;
+    res->q[1] = T.q.j;
+    res->q[2] = T.q.k;
+    res->q[3] = T.q.w;
+    res->mse = mse;
+    res->iterations = iters;
+    res->converged = converged;
+    res->n_corr = pairs.size();
+    if (pairs_out)
+      for (size_t i = 0; i < pairs.size(); ++i) {
+        pairs_out[2 * i] = pairs[i].first;
+        pairs_out[2 * i + 1] = pairs[i].second;
+      }
+  };
+  int status = 0;
+  for (uint64_t iteration = 0; iteration < max_iters; ++iteration) {
+    for (uint64_t i = 0; i < ns; ++i)
+      ts[i] = iso_apply(T, V3{src[3 * i], src[3 * i + 1], src[3 * i + 2]});
+    const M3 R = quat_to_matrix(T.q);
+    const M3 Rt = m3_t(R);
+    // the reference's 1-NN loop is serial (gicp.rs:200-255); the queries are independent, so
+    // they are run in parallel here and consumed in order
+#pragma omp parallel num_threads(nth)
+    {
+      std::vector<Neighbor> out;
+      std::vector<uint32_t> stack;
+#pragma omp for schedule(dynamic, 256)
+      for (int64_t i = 0; i < (int64_t)ns; ++i) {
+        kd_find_k_nearest(*tree, P3{ts[i].x, ts[i].y, ts[i].z}, 1, out, stack);
+        corr_idx[i] = out.empty() ? -1 : (int64_t)out[0].index;
+        corr_dist[i] = out.empty() ? 0.0f : std::sqrt(out[0].distance);
+      }
+    }
+    float h[6][6];
+    float g[6];
+    std::memset(h, 0, sizeof(h));
+    std::memset(g, 0, sizeof(g));
+    uint64_t n_corr = 0;
+    float mse_sum = 0.0f;
+    corr_pairs.clear();
+    for (uint64_t i = 0; i < ns; ++i) {
+      if (corr_idx[i] < 0) continue;
+      const float dist = corr_dist[i];
+      if (dist > max_dist) continue;
+      const uint64_t j = (uint64_t)corr_idx[i];
+      const M3 rc = m3_mul(m3_mul(R, scov[i]), Rt);
+      M3 m;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) m.m[r][c] = tcov[j].m[r][c] + rc.m[r][c];
+      M3 mi;
+      if (!m3_try_inverse(m, mi)) continue;
+      const V3 resid{tgt[3 * j] - ts[i].x, tgt[3 * j + 1] - ts[i].y, tgt[3 * j + 2] - ts[i].z};
+      const M3 a = neg_skew(ts[i]);
+      const M3 at = m3_t(a);
+      const M3 h_rr = m3_mul(at, m3_mul(mi, a));
+      const M3 h_rt = m3_mul(at, mi);
+      const V3 wr = m3_vec(mi, resid);
+      const V3 g_r = m3_vec(at, wr);
+      const float grv[3] = {g_r.x, g_r.y, g_r.z}, wrv[3] = {wr.x, wr.y, wr.z};
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) {
+          h[r][c] += h_rr.m[r][c];
+          h[r][c + 3] += h_rt.m[r][c];
+          h[r + 3][c] += h_rt.m[c][r];
+          h[r + 3][c + 3] += mi.m[r][c];
+        }
+        g[r] += grv[r];
+        g[r + 3] += wrv[r];
+      }
+      n_corr += 1;
+      mse_sum += dist * dist;
+      corr_pairs.emplace_back(i, j);
+    }
+    if (n_corr < 6) {
+      status = 2;
+      break;
+    }
+    const float mse = mse_sum / (float)n_corr;
+    float x[6];
+    {
+      float L[6][6];
+      std::memcpy(L, h, sizeof(L));
+      std::memcpy(x, g, sizeof(x));
+      if (cholesky6(L)) {
+        cholesky6_solve(L, x);
+      } else {
+        std::memcpy(L, h, sizeof(L));
+        std::memcpy(x, g, sizeof(x));
+        if (!lu6_solve(L, x)) {
+          status = 3;
+          break;
+        }
+      }
+    }
+    const Quat rx = quat_axis_angle(0, x[0]);
+    const Quat ry = quat_axis_angle(1, x[1]);
+    const Quat rz = quat_axis_angle(2, x[2]);
+    const Iso delta{quat_mul(quat_mul(rz, ry), rx), V3{x[3], x[4], x[5]}};
+    T = iso_mul(delta, T);
+    if (std::fabs(prev_mse - mse) < conv) {
+      finish(mse, iteration + 1, 1, corr_pairs);
+      delete tree;
+      return 0;
+    }
+    prev_mse = mse;
+    final_corr = corr_pairs;
+  }
+  delete tree;
+  if (status != 0) return status;
+  finish(prev_mse, max_iters, 0, final_corr);
+  return 0;
+}
+
+// per-point GICP covariances (row-major 3x3 per point), for kernel-level parity checks
+void orc_gicp_covariances(const float* xyz, uint64_t n, uint64_t k, float* cov9_out, int threads) {
+  std::vector<M3> covs;
+  gicp_covariances(xyz, n, k, covs, threads > 0 ? threads : orc_max_threads());
+  for (uint64_t i = 0; i < n; ++i) std::memcpy(cov9_out + 9 * i, covs[i].m, 9 * sizeof(float));
+}
+}  // extern "C"

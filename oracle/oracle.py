@@ -72,6 +72,11 @@ def _load():
     lib.orc_iso_mul.argtypes = [_f32p, _f32p, _f32p]
     lib.orc_solve6.restype = C.c_int
     lib.orc_solve6.argtypes = [_f32p, _f32p, _f32p]
+    lib.orc_gicp.restype = C.c_int
+    lib.orc_gicp.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_uint64, C.c_float,
+                             C.c_float, C.c_uint64, C.POINTER(_IcpRes), _u64p,
+                             C.POINTER(C.c_int), C.c_int]
+    lib.orc_gicp_covariances.argtypes = [_f32p, C.c_uint64, C.c_uint64, _f32p, C.c_int]
     _lib = lib
     return lib
 
@@ -281,3 +286,43 @@ def solve6(ata, atb):
     x = np.empty(6, np.float32)
     st = _load().orc_solve6(_p(_f32(ata, (36,)), _f32p), _p(_f32(atb, (6,)), _f32p), _p(x, _f32p))
     return x, st
+
+
+def gicp_covariances(points, k: int = 20, threads: int = 0) -> np.ndarray:
+    """compute_covariances (gicp.rs:58-95) -> [n, 3, 3] f32."""
+    pts = _f32(points, (-1, 3))
+    out = np.empty((pts.shape[0], 3, 3), np.float32)
+    _load().orc_gicp_covariances(_p(pts, _f32p), pts.shape[0], int(k), _p(out, _f32p), threads)
+    return out
+
+
+_GICP_INVALID = {1: "GICP: source or target point cloud is empty",
+                 2: "GICP: max_iterations must be > 0",
+                 3: "GICP: clouds must have at least k points for reliable covariance estimation",
+                 4: "GICP: source point cloud appears to be coplanar or collinear",
+                 5: "GICP: target point cloud appears to be coplanar or collinear"}
+
+
+def gicp(source, target, init=None, max_iterations: int = 50,
+         max_correspondence_distance: float = 1.0, convergence_threshold: float = 1e-6,
+         k_correspondences: int = 20, threads: int = 0) -> IcpResult:
+    """gicp (gicp.rs:117-312) with GicpConfig's defaults (:37-46)."""
+    src = _f32(source, (-1, 3))
+    tgt = _f32(target, (-1, 3))
+    init7 = _f32([0, 0, 0, 0, 0, 0, 1] if init is None else init, (7,))
+    res = _IcpRes()
+    why = C.c_int(0)
+    pairs = np.zeros((max(src.shape[0], 1), 2), np.uint64)
+    st = _load().orc_gicp(_p(src, _f32p), src.shape[0], _p(tgt, _f32p), tgt.shape[0],
+                          _p(init7, _f32p), int(max_iterations), float(max_correspondence_distance),
+                          float(convergence_threshold), int(k_correspondences), C.byref(res),
+                          _p(pairs, _u64p), C.byref(why), threads)
+    if st == 1:
+        raise InvalidData(_GICP_INVALID.get(why.value, "GICP: invalid arguments"))
+    if st == 2:
+        raise AlgorithmError("GICP: insufficient correspondences (need >= 6)")
+    if st == 3:
+        raise AlgorithmError("GICP: Gauss-Newton system is ill-conditioned")
+    return IcpResult(np.array(res.t[:], np.float32), np.array(res.q[:], np.float32),
+                     float(res.mse), int(res.iterations), bool(res.converged),
+                     pairs[: res.n_corr].copy())

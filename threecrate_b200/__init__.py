@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     Comm,
     Context,
     DeviceCloud,
+    GicpConfig,
     GpuError,
     GridIndex,
     ICPResult,
@@ -29,6 +30,7 @@ from .api import (  # noqa: F401
     estimate_normals,
     estimate_normals_radius,
     estimate_normals_with_config,
+    gicp,
     icp,
     icp_detailed,
     icp_point_to_plane,

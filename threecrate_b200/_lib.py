@@ -94,6 +94,8 @@ SYMBOLS = {
                                         C.c_float, C.c_float, C.POINTER(IcpResultC), _vp]),
     "tc_icp_point_to_point_device": (C.c_int, [_vp, _vp, _vp, _vp, _f32p, C.c_uint32, C.c_float,
                                                C.c_float, C.POINTER(IcpResultC), _vp]),
+    "tc_gicp": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _f32p, C.c_uint32, C.c_float,
+                          C.c_float, C.c_uint32, C.POINTER(IcpResultC), _vp]),
     "tc_multiscale_icp_point_to_point": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _f32p,
                                                    C.POINTER(IcpScaleLevelC), C.c_uint32,
                                                    C.c_uint32, C.c_float, C.c_float,

@@ -584,6 +584,38 @@ def multiscale_icp_point_to_point(source, target, init=IDENTITY,
 
 
 # --------------------------------------------------------------------------------------------
+# Generalized ICP (threecrate-algorithms/src/gicp.rs)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class GicpConfig:
+    """gicp.rs:24-46"""
+    max_iterations: int = 50
+    max_correspondence_distance: float = 1.0
+    convergence_threshold: float = 1e-6
+    k_correspondences: int = 20
+
+
+def gicp(source, target, init=IDENTITY, config: Optional[GicpConfig] = None,
+         ctx: Optional[Context] = None, want_correspondences: bool = True) -> ICPResult:
+    """gicp.rs:117-312"""
+    config = config or GicpConfig()
+    src, tgt = _pts(source, "source"), _pts(target, "target")
+    init7 = np.ascontiguousarray(init, np.float32).reshape(7)
+    ctx = ctx or default_context()
+    res = _lib.IcpResultC()
+    pairs = np.zeros((max(src.shape[0], 1), 2), np.uint64) if want_correspondences else None
+    ctx.check(ctx.lib.tc_gicp(
+        ctx.h, _vp(src.ctypes.data), src.shape[0], _vp(tgt.ctypes.data), tgt.shape[0],
+        init7.ctypes.data_as(C.POINTER(C.c_float)), int(config.max_iterations),
+        float(config.max_correspondence_distance), float(config.convergence_threshold),
+        int(config.k_correspondences), C.byref(res),
+        None if pairs is None else _vp(pairs.ctypes.data)))
+    corr = pairs[: res.n_correspondences].copy() if pairs is not None else np.empty((0, 2), np.uint64)
+    return ICPResult(np.array(res.transform[:], np.float32), float(res.mse), int(res.iterations),
+                     bool(res.converged), corr)
+
+
+# --------------------------------------------------------------------------------------------
 # multi-GPU (one process per GPU)
 # --------------------------------------------------------------------------------------------
 class Comm:

@@ -640,3 +640,80 @@ extern "C" int tc_multiscale_icp_point_to_point(
   tc_cloud_free(src);
   return st;
 }
+
+// gicp (gicp.rs:117-312): validation in the reference's order, per-point covariances of both
+// clouds (kNN(k) incl. self), then the Gauss-Newton loop on the device.
+extern "C" int tc_gicp(tc_context* ctx, const float* src_aos, uint64_t ns, const float* tgt_aos,
+                       uint64_t nt, const float init[7], uint32_t max_iterations,
+                       float max_correspondence_distance, float convergence_threshold,
+                       uint32_t k_correspondences, tc_icp_result* out, uint64_t* pairs_out) {
+  TC_ENTER(ctx);
+  if (ns == 0 || nt == 0)
+    return tc_fail(ctx, TC_INVALID_DATA, "GICP: source or target point cloud is empty");
+  if (max_iterations == 0) return tc_fail(ctx, TC_INVALID_DATA, "GICP: max_iterations must be > 0");
+  const uint32_t min_k = std::max<uint32_t>(k_correspondences, 4);
+  if (ns < min_k || nt < min_k)
+    return tc_fail(ctx, TC_INVALID_DATA,
+                   "GICP: clouds must have at least " + std::to_string(min_k) +
+                       " points for reliable covariance estimation (k_correspondences=" +
+                       std::to_string(k_correspondences) + "); got source=" + std::to_string(ns) +
+                       ", target=" + std::to_string(nt));
+  if (min_k > 64)
+    return tc_fail(ctx, TC_INVALID_DATA, "GICP: k_correspondences > 64 exceeds the device top-k");
+  if (!src_aos || !tgt_aos || !init || !out) return TC_INVALID_DATA;
+  tc_cloud *src = nullptr, *tgt = nullptr;
+  tc_index* ix = nullptr;
+  float4 *d_scov = nullptr, *d_tcov = nullptr;
+  uint32_t* d_match = nullptr;
+  int st = tc_cloud_upload(ctx, src_aos, ns, &src);
+  if (st == TC_OK) st = tc_cloud_upload(ctx, tgt_aos, nt, &tgt);
+  // coplanar / collinear clouds are rejected by their bounding box (gicp.rs:148-166)
+  for (int which = 0; which < 2 && st == TC_OK; ++which) {
+    const tc_cloud* c = which == 0 ? src : tgt;
+    float mn[3], mx[3];
+    st = tci_bbox(ctx, c->d_xyz, c->n, mn, mx);
+    if (st != TC_OK) break;
+    float min_extent = INFINITY;
+    for (int a = 0; a < 3; ++a) min_extent = std::fmin(min_extent, mx[a] - mn[a]);
+    if (min_extent < 1e-4f) {
+      char buf[32];
+      snprintf(buf, sizeof(buf), "%.2e", (double)min_extent);
+      st = tc_fail(ctx, TC_INVALID_DATA,
+                   std::string("GICP: ") + (which == 0 ? "source" : "target") +
+                       " point cloud appears to be coplanar or collinear (smallest bounding-box "
+                       "dimension = " + buf + "); GICP requires 3-D structure");
+    }
+  }
+  if (st == TC_OK) st = tci_gicp_covariances(ctx, src, min_k, &d_scov);
+  if (st == TC_OK) st = tci_gicp_covariances(ctx, tgt, min_k, &d_tcov);
+  if (st == TC_OK) st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);
+  if (st == TC_OK && pairs_out) st = tc_alloc(ctx, &d_match, ns);
+  if (st == TC_OK)
+    st = tci_gicp_device(ctx, src, ix, d_scov, d_tcov, init, max_iterations,
+                         max_correspondence_distance, convergence_threshold, out, d_match);
+  if (st == TC_OK && pairs_out) {
+    std::vector<uint32_t> match(ns);
+    cudaError_t e = cudaMemcpyAsync(match.data(), d_match, ns * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      st = tc_fail(ctx, TC_GPU, std::string("GICP pairs: ") + cudaGetErrorString(e));
+    } else {
+      uint64_t c = 0;
+      for (uint64_t i = 0; i < ns; ++i)
+        if (match[i] != TC_NO_INDEX) {
+          pairs_out[2 * c] = i;
+          pairs_out[2 * c + 1] = match[i];
+          ++c;
+        }
+      out->n_correspondences = c;
+    }
+  }
+  tc_free(ctx, d_match);
+  tc_free(ctx, d_scov);
+  tc_free(ctx, d_tcov);
+  tc_index_free(ix);
+  tc_cloud_free(tgt);
+  tc_cloud_free(src);
+  return st;
+}

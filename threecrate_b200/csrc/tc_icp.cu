@@ -31,7 +31,7 @@ using namespace tcs;
 constexpr int kIcpBlock = 256;
 constexpr int kNumSums = 29;   // point-to-plane: 21 AtA + 6 Atb + sum b^2 + n_valid
 constexpr int kNumSumsP2P = 17; // point-to-point: sum s (3) + sum t (3) + sum s t^T (9) + sum |s-t|^2 + n
-constexpr int kPlane = 0, kPoint = 1;
+constexpr int kPlane = 0, kPoint = 1, kGicp = 2;  // kGicp: same 29 sums as kPlane (H, g, sum d^2, n)
 
 struct IcpState {
   float T[7];          // tx,ty,tz, qi,qj,qk,qw
@@ -113,10 +113,13 @@ k_pad_normals(const float* __restrict__ nrm, uint32_t n, float4* __restrict__ ou
   }
 }
 
+// tgt_nrm: target normals (kPlane) or target covariances, two float4 per point (kGicp);
+// src_cov: source covariances, two float4 per point by ORIGINAL source index (kGicp)
 template <int MODE>
-__global__ void __launch_bounds__(kIcpBlock, 4)  // 64 registers: the called solve may spill freely
+__global__ void __launch_bounds__(kIcpBlock, MODE == kGicp ? 2 : 4)  // 64 registers (the called
+                                                                      // solve may spill freely)
 k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
-                 const float4* __restrict__ src, uint32_t ns,
+                 const float4* __restrict__ src_cov, const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
                  double* __restrict__ sums, uint32_t* __restrict__ match_out,
                  uint32_t* __restrict__ prev, int fuse, PeerXchg px, int solve_here, float conv) {
@@ -129,15 +132,34 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   // ends up with the warp's total of sum j) and adds that to ONE f64 register per lane - instead
   // of carrying NS accumulators per thread through the search, which cost 29 registers and a
   // third of the occupancy.  Everything across warps, blocks and ranks is reduced in f64.
-  constexpr int NS = MODE == kPlane ? kNumSums : kNumSumsP2P;
+  constexpr int NS = MODE == kPoint ? kNumSumsP2P : kNumSums;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
+  float R[3][3];  // rotation of T (UnitQuaternion::to_rotation_matrix), kGicp only
+  if (MODE == kGicp) {
+    const float qi = T[3], qj = T[4], qk = T[5], qw = T[6];
+    const float ww = xmul(qw, qw), ii = xmul(qi, qi), jj = xmul(qj, qj), kk = xmul(qk, qk);
+    const float ij = xmul(xmul(qi, qj), 2.0f), wk = xmul(xmul(qw, qk), 2.0f),
+                wj = xmul(xmul(qw, qj), 2.0f), ik = xmul(xmul(qi, qk), 2.0f),
+                jk = xmul(xmul(qj, qk), 2.0f), wi = xmul(xmul(qw, qi), 2.0f);
+    R[0][0] = xsub(xsub(xadd(ww, ii), jj), kk);
+    R[0][1] = xsub(ij, wk);
+    R[0][2] = xadd(wj, ik);
+    R[1][0] = xadd(wk, ij);
+    R[1][1] = xsub(xadd(xsub(ww, ii), jj), kk);
+    R[1][2] = xsub(jk, wi);
+    R[2][0] = xsub(ik, wj);
+    R[2][1] = xadd(wi, jk);
+    R[2][2] = xadd(xsub(xsub(ww, ii), jj), kk);
+  }
 
   for (uint32_t i0 = blockIdx.x * kIcpBlock + warp * 32; i0 < ns; i0 += gridDim.x * kIcpBlock) {
     const uint32_t i = i0 + lane;
     bool valid = false;
     V3 s{0.0f, 0.0f, 0.0f};
     float4 d4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    uint32_t sid = 0, tid = TC_NO_INDEX;  // original indices of the source point and its match
+    float nn_d2 = 0.0f;
     if (i < ns) {
       const float4 s4 = __ldg(&src[i]);
       // current_transform * p  (registration.rs:540-544)
@@ -193,8 +215,12 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
       if (valid && max_dist >= 0.0f) {  // reject iff distance > max (registration.rs:100)
         if (xsqrt(best.kth()) > max_dist) valid = false;
       }
-      if (match_out) match_out[__float_as_uint(s4.w)] = valid ? (uint32_t)best.key : TC_NO_INDEX;
-      if (valid) d4 = __ldg(&ls.pts[level][best.pos]);
+      sid = __float_as_uint(s4.w);
+      if (valid) {
+        d4 = __ldg(&ls.pts[level][best.pos]);
+        tid = (uint32_t)best.key;
+        nn_d2 = best.kth();
+      }
     }
     float v[32];
 #pragma unroll
@@ -215,6 +241,91 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
       for (int r = 0; r < 6; ++r) v[21 + r] = xmul(a[r], b);
       v[27] = xmul(b, b);
       v[28] = valid ? 1.0f : 0.0f;
+    } else if (MODE == kGicp) {
+      // gicp.rs:204-252: M = C_t + R C_s R^T, M^-1 by the adjugate formula (a singular M skips
+      // the pair), J = [-skew(T s) | I]; sums = lower triangle of H, g, sum dist^2, n.
+      // 3x3 products accumulate (a0 b0 + a1 b1) + a2 b2 like nalgebra's.
+      float Cs[3][3], M[3][3];
+      {
+        float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+        if (valid) {
+          a0 = __ldg(&src_cov[2 * (uint64_t)sid]);
+          a1 = __ldg(&src_cov[2 * (uint64_t)sid + 1]);
+          b0 = __ldg(&tgt_nrm[2 * (uint64_t)tid]);
+          b1 = __ldg(&tgt_nrm[2 * (uint64_t)tid + 1]);
+        }
+        Cs[0][0] = a0.x; Cs[0][1] = a0.y; Cs[0][2] = a0.z;
+        Cs[1][0] = a0.y; Cs[1][1] = a0.w; Cs[1][2] = a1.x;
+        Cs[2][0] = a0.z; Cs[2][1] = a1.x; Cs[2][2] = a1.y;
+        float t[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            t[r][c] = xadd(xadd(xmul(R[r][0], Cs[0][c]), xmul(R[r][1], Cs[1][c])), xmul(R[r][2], Cs[2][c]));
+        const float Ct[3][3] = {{b0.x, b0.y, b0.z}, {b0.y, b0.w, b1.x}, {b0.z, b1.x, b1.y}};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            M[r][c] = xadd(Ct[r][c], xadd(xadd(xmul(t[r][0], R[c][0]), xmul(t[r][1], R[c][1])),
+                                          xmul(t[r][2], R[c][2])));
+      }
+      float mi[3][3];
+      {
+        const float m11 = M[0][0], m12 = M[0][1], m13 = M[0][2], m21 = M[1][0], m22 = M[1][1],
+                    m23 = M[1][2], m31 = M[2][0], m32 = M[2][1], m33 = M[2][2];
+        const float n1223 = xsub(xmul(m22, m33), xmul(m32, m23));
+        const float n1123 = xsub(xmul(m21, m33), xmul(m31, m23));
+        const float n1122 = xsub(xmul(m21, m32), xmul(m31, m22));
+        const float det = xadd(xsub(xmul(m11, n1223), xmul(m12, n1123)), xmul(m13, n1122));
+        if (det == 0.0f) valid = false;  // try_inverse() == None (all-zero input when unmatched)
+        mi[0][0] = xdiv(n1223, det);
+        mi[0][1] = xdiv(xsub(xmul(m13, m32), xmul(m33, m12)), det);
+        mi[0][2] = xdiv(xsub(xmul(m12, m23), xmul(m22, m13)), det);
+        mi[1][0] = xdiv(-n1123, det);
+        mi[1][1] = xdiv(xsub(xmul(m11, m33), xmul(m31, m13)), det);
+        mi[1][2] = xdiv(xsub(xmul(m13, m21), xmul(m23, m11)), det);
+        mi[2][0] = xdiv(n1122, det);
+        mi[2][1] = xdiv(xsub(xmul(m12, m31), xmul(m32, m11)), det);
+        mi[2][2] = xdiv(xsub(xmul(m11, m22), xmul(m21, m12)), det);
+      }
+      const float rs[3] = {xsub(d4.x, s.x), xsub(d4.y, s.y), xsub(d4.z, s.z)};  // t_i - T s_i
+      const float A[3][3] = {{-0.0f, s.z, -s.y}, {-s.z, -0.0f, s.x}, {s.y, -s.x, -0.0f}};
+      float ma[3][3], hrr[3][3], hrt[3][3], wr[3], gr[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ma[r][c] = xadd(xadd(xmul(mi[r][0], A[0][c]), xmul(mi[r][1], A[1][c])), xmul(mi[r][2], A[2][c]));
+        wr[r] = xadd(xadd(xmul(mi[r][0], rs[0]), xmul(mi[r][1], rs[1])), xmul(mi[r][2], rs[2]));
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {  // A^T (.)  : A^T[r][k] = A[k][r]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          hrr[r][c] = xadd(xadd(xmul(A[0][r], ma[0][c]), xmul(A[1][r], ma[1][c])), xmul(A[2][r], ma[2][c]));
+          hrt[r][c] = xadd(xadd(xmul(A[0][r], mi[0][c]), xmul(A[1][r], mi[1][c])), xmul(A[2][r], mi[2][c]));
+        }
+        gr[r] = xadd(xadd(xmul(A[0][r], wr[0]), xmul(A[1][r], wr[1])), xmul(A[2][r], wr[2]));
+      }
+      // upper-triangle slot (r <= c) of the 21 <- the LOWER element H[c][r] the Cholesky reads
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+          const float h = c < 3 ? hrr[c][r] : (r < 3 ? hrt[r][c - 3] : mi[c - 3][r - 3]);
+          v[r * 6 - (r * (r - 1)) / 2 + (c - r)] = valid ? h : 0.0f;
+        }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        v[21 + r] = valid ? gr[r] : 0.0f;
+        v[24 + r] = valid ? wr[r] : 0.0f;
+      }
+      const float dist = xsqrt(nn_d2);
+      v[27] = valid ? xmul(dist, dist) : 0.0f;  // mse_sum += dist * dist (gicp.rs:256)
+      v[28] = valid ? 1.0f : 0.0f;
+      if (!valid) tid = TC_NO_INDEX;
     } else {
       // raw moments for Kabsch (registration.rs:157-172) and the mse (:206-218)
       const float m = valid ? 1.0f : 0.0f;
@@ -230,6 +341,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
       v[15] = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
       v[16] = m;
     }
+    if (match_out && i < ns) match_out[sid] = valid ? tid : TC_NO_INDEX;
     // transpose-reduce: after the step with offset o a lane holds the values whose index has the
     // same o-bit as its lane id, summed over the lane pair; five steps leave lane j with sum j
 #pragma unroll
@@ -316,8 +428,8 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
     if (solve_here) {
       __syncthreads();
       if (threadIdx.x == 0) {
-        if (MODE == kPlane) icp_solve_plane(st, sums, conv);
-        else icp_solve_point(st, sums, conv);
+        if (MODE == kPoint) icp_solve_point(st, sums, conv);
+        else icp_solve_plane(st, sums, conv);  // kGicp: same 6x6 system layout and update
       }
     }
   }
@@ -599,10 +711,13 @@ k_icp_p2p_final_mse(LevelSet ls, const float4* __restrict__ src, uint32_t ns,
 namespace {
 
 // Shared driver of the device-resident ICP loops (mode: kPlane / kPoint).
+// d_tgt_normals_aos: target normals n x 3 (kPlane).  d_src_cov / d_tgt_cov: per-point covariances
+// as two float4 {xx, xy, xz, yy | yz, zz, 0, 0} by original index (kGicp).
 int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* src,
-                    const tc_index* tgt, const float* d_tgt_normals_aos, const float init[7],
-                    uint32_t max_iters, float max_corr_dist, float conv_threshold,
-                    tc_icp_result* out, uint32_t* d_match_out) {
+                    const tc_index* tgt, const float* d_tgt_normals_aos, const float4* d_src_cov,
+                    const float4* d_tgt_cov, const float init[7], uint32_t max_iters,
+                    float max_corr_dist, float conv_threshold, tc_icp_result* out,
+                    uint32_t* d_match_out) {
   if (!ctx || !src || !tgt || !out || !init) return TC_INVALID_DATA;
   // validation order of registration.rs:266-276 / 517-531 (normals length: host wrapper)
   if ((src->n == 0 && !comm) || tgt->n == 0)
@@ -610,6 +725,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   if (mode == kPlane && !d_tgt_normals_aos)
     return tc_fail(ctx, TC_INVALID_DATA,
                    "target_normals length must equal the number of target points");
+  if (mode == kGicp && (!d_src_cov || !d_tgt_cov)) return TC_INVALID_DATA;
   if (max_iters == 0) return tc_fail(ctx, TC_INVALID_DATA, "Max iterations must be positive");
   const uint32_t ns = (uint32_t)src->n;
   const uint32_t nt = (uint32_t)tgt->n;
@@ -677,21 +793,25 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
       fuse = 1;
     const int solve_here = (!comm || fuse) && g_tc_icp_solve_fused ? 1 : 0;
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
-      if (mode == kPlane)
+      if (mode == kGicp)
+        k_icp_correspond<kGicp><<<grid, kIcpBlock, 0, ctx->stream>>>(
+            ls, d_tgt_cov, d_src_cov, d_src, ns, max_corr_dist, d_state, d_partials, d_sums,
+            d_match_out, d_prev, fuse, px, solve_here, conv_threshold);
+      else if (mode == kPlane)
         k_icp_correspond<kPlane><<<grid, kIcpBlock, 0, ctx->stream>>>(
-            ls, d_nrm, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev,
+            ls, d_nrm, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev,
             fuse, px, solve_here, conv_threshold);
       else
         k_icp_correspond<kPoint><<<grid, kIcpBlock, 0, ctx->stream>>>(
-            ls, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out,
+            ls, nullptr, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out,
             d_prev, fuse, px, solve_here, conv_threshold);
       ctx->launches++;
       if (solve_here) continue;
       st = tci_comm_allreduce(comm, d_sums, n_sums);
-      if (mode == kPlane)
-        k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
-      else
+      if (mode == kPoint)
         k_icp_solve_p2p<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
+      else
+        k_icp_solve<<<1, 32, 0, ctx->stream>>>(d_state, d_sums, conv_threshold);
       ctx->launches++;
     }
     if (st == TC_OK && mode == kPoint) {
@@ -727,17 +847,19 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   if (st != TC_OK) return st;
   if (h_state.status == 2)
     return tc_fail(ctx, TC_ALGORITHM,
-                   mode == kPlane ? "Insufficient correspondences for point-to-plane ICP (need >= 6)"
-                                  : "Insufficient correspondences found");
+                   mode == kPlane  ? "Insufficient correspondences for point-to-plane ICP (need >= 6)"
+                   : mode == kGicp ? "GICP: insufficient correspondences (need >= 6)"
+                                   : "Insufficient correspondences found");
   if (h_state.status == 4)
     return tc_fail(ctx, TC_GPU, "ICP peer exchange timed out (a rank did not arrive)");
   if (h_state.status == 3)
-    return tc_fail(ctx, TC_ALGORITHM, mode == kPlane ? "Point-to-plane system is ill-conditioned"
+    return tc_fail(ctx, TC_ALGORITHM, mode == kPlane  ? "Point-to-plane system is ill-conditioned"
+                                      : mode == kGicp ? "GICP: Gauss-Newton system is ill-conditioned"
                                                       : "SVD of the cross-covariance failed");
   for (int i = 0; i < 7; ++i) out->transform[i] = h_state.T[i];
   if (h_state.converged) {
     out->mse = h_state.mse;
-  } else if (mode == kPlane) {
+  } else if (mode != kPoint) {
     out->mse = h_state.prev_mse;  // previous_mse == the last iteration's mse (:595-601)
   } else {
     out->mse = h_final[1] > 0.0 ? (float)(h_final[0] / h_final[1]) : h_state.prev_mse;
@@ -758,8 +880,8 @@ extern "C" int tc_icp_point_to_plane_device(tc_context* ctx, tc_comm* comm, cons
                                             const float init[7], uint32_t max_iters,
                                             float max_corr_dist, float conv_threshold,
                                             tc_icp_result* out, uint32_t* d_match_out) {
-  return icp_device_impl(kPlane, ctx, comm, src, tgt, d_tgt_normals_aos, init, max_iters,
-                         max_corr_dist, conv_threshold, out, d_match_out);
+  return icp_device_impl(kPlane, ctx, comm, src, tgt, d_tgt_normals_aos, nullptr, nullptr, init,
+                         max_iters, max_corr_dist, conv_threshold, out, d_match_out);
 }
 
 extern "C" int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, const tc_cloud* src,
@@ -767,6 +889,86 @@ extern "C" int tc_icp_point_to_point_device(tc_context* ctx, tc_comm* comm, cons
                                             uint32_t max_iters, float max_corr_dist,
                                             float conv_threshold, tc_icp_result* out,
                                             uint32_t* d_match_out) {
-  return icp_device_impl(kPoint, ctx, comm, src, tgt, nullptr, init, max_iters, max_corr_dist,
-                         conv_threshold, out, d_match_out);
+  return icp_device_impl(kPoint, ctx, comm, src, tgt, nullptr, nullptr, nullptr, init, max_iters,
+                         max_corr_dist, conv_threshold, out, d_match_out);
+}
+
+// ---------------------------------------------------------------------------------- GICP
+// compute_covariances (gicp.rs:58-95) from kNN rows (k neighbours INCLUDING the point itself,
+// ascending (d2, index)): mean by sequential f32 adds, outer products accumulated in neighbour
+// order, / max(n - 1, 1), + 1e-4 I; fewer than 3 neighbours -> 1e-3 I.
+__global__ void __launch_bounds__(256) k_gicp_cov(const float* __restrict__ xyz, uint32_t n,
+                                                  uint32_t k, const uint32_t* __restrict__ idx,
+                                                  float4* __restrict__ cov) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t* row = idx + (uint64_t)i * k;
+    uint32_t m = 0;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (uint32_t j = 0; j < k; ++j) {
+      const uint32_t id = row[j];
+      if (id == TC_NO_INDEX) break;
+      sx = xadd(sx, xyz[3 * (uint64_t)id]);
+      sy = xadd(sy, xyz[3 * (uint64_t)id + 1]);
+      sz = xadd(sz, xyz[3 * (uint64_t)id + 2]);
+      ++m;
+    }
+    float c[6] = {1e-3f, 0.0f, 0.0f, 1e-3f, 0.0f, 1e-3f};  // xx xy xz yy yz zz
+    if (m >= 3) {
+      const float nf = (float)m;
+      const float mx = xdiv(sx, nf), my = xdiv(sy, nf), mz = xdiv(sz, nf);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) c[t] = 0.0f;
+      for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t id = row[j];
+        const float dx = xsub(xyz[3 * (uint64_t)id], mx), dy = xsub(xyz[3 * (uint64_t)id + 1], my),
+                    dz = xsub(xyz[3 * (uint64_t)id + 2], mz);
+        c[0] = xadd(c[0], xmul(dx, dx));
+        c[1] = xadd(c[1], xmul(dx, dy));
+        c[2] = xadd(c[2], xmul(dx, dz));
+        c[3] = xadd(c[3], xmul(dy, dy));
+        c[4] = xadd(c[4], xmul(dy, dz));
+        c[5] = xadd(c[5], xmul(dz, dz));
+      }
+      const float den = fmaxf(xsub(nf, 1.0f), 1.0f);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) c[t] = xdiv(c[t], den);
+      c[0] = xadd(c[0], 1e-4f);
+      c[3] = xadd(c[3], 1e-4f);
+      c[5] = xadd(c[5], 1e-4f);
+    }
+    cov[2 * (uint64_t)i] = make_float4(c[0], c[1], c[2], c[3]);
+    cov[2 * (uint64_t)i + 1] = make_float4(c[4], c[5], 0.0f, 0.0f);
+  }
+}
+
+int tci_gicp_covariances(tc_context* ctx, const tc_cloud* cloud, uint32_t k, float4** d_cov) {
+  *d_cov = nullptr;
+  const uint32_t n = (uint32_t)cloud->n;
+  tc_index* ix = nullptr;
+  TC_TRY(tc_index_build(ctx, cloud, k, 0.0f, &ix));
+  uint32_t* d_idx = nullptr;
+  int st = tc_alloc(ctx, &d_idx, (uint64_t)n * k);
+  if (st == TC_OK) st = tc_alloc(ctx, d_cov, 2 * (uint64_t)n);
+  if (st == TC_OK) st = tci_knn_launch(ctx, ix, nullptr, 0, n, k, 0, true, d_idx, nullptr, nullptr);
+  if (st == TC_OK) {
+    k_gicp_cov<<<std::max(1, std::min((int)((n + 255) / 256), ctx->sm_count * 8)), 256, 0,
+                 ctx->stream>>>(cloud->d_xyz, n, k, d_idx, *d_cov);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "covariance launch failed");
+  }
+  tc_free(ctx, d_idx);
+  tc_index_free(ix);
+  if (st != TC_OK) {
+    tc_free(ctx, *d_cov);
+    *d_cov = nullptr;
+  }
+  return st;
+}
+
+int tci_gicp_device(tc_context* ctx, const tc_cloud* src, const tc_index* tgt,
+                    const float4* d_src_cov, const float4* d_tgt_cov, const float init[7],
+                    uint32_t max_iters, float max_corr_dist, float conv_threshold,
+                    tc_icp_result* out, uint32_t* d_match_out) {
+  return icp_device_impl(kGicp, ctx, nullptr, src, tgt, nullptr, d_src_cov, d_tgt_cov, init,
+                         max_iters, max_corr_dist, conv_threshold, out, d_match_out);
 }

@@ -149,6 +149,15 @@ int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radi
 int tci_radius_search_launch(tc_context* ctx, const tc_index* index, const float q[3], float radius,
                              uint32_t* d_idx, float* d_d2, uint32_t capacity, uint32_t* d_count);
 
+// tc_icp.cu — GICP building blocks (gicp.rs): per-point covariances as two float4
+// {xx, xy, xz, yy | yz, zz, 0, 0} by original index, and the Gauss-Newton loop
+struct tc_icp_result;
+int tci_gicp_covariances(tc_context* ctx, const tc_cloud* cloud, uint32_t k, float4** d_cov);
+int tci_gicp_device(tc_context* ctx, const tc_cloud* src, const tc_index* tgt,
+                    const float4* d_src_cov, const float4* d_tgt_cov, const float init[7],
+                    uint32_t max_iters, float max_corr_dist, float conv_threshold,
+                    tc_icp_result* out, uint32_t* d_match_out);
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
