@@ -6,7 +6,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("THREECRATE_CUDA_CSRC").unwrap_or_else(|_| "csrc".into()));
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["tc_api.cu", "tc_index.cu", "tc_search.cu", "tc_icp.cu", "tc_comm.cu"];
+    let sources = ["tc_api.cu", "tc_index.cu", "tc_search.cu", "tc_icp.cu", "tc_comm.cu", "tc_filter.cu"];
     let mut objs = Vec::new();
     for s in sources {
         let o = out.join(s.replace(".cu", ".o"));

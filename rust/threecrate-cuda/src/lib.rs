@@ -45,7 +45,30 @@ extern "C" {
                              nrm: *const f32, nn: u64, init: *const f32, max_iters: u32,
                              max_dist: f32, conv: f32, out: *mut TcIcpResult,
                              pairs: *mut u64) -> c_int;
+    fn tc_icp_point_to_point(ctx: *mut TcContext, src: *const f32, ns: u64, tgt: *const f32, nt: u64,
+                             init: *const f32, max_iters: u32, max_dist: f32, conv: f32,
+                             out: *mut TcIcpResult, pairs: *mut u64) -> c_int;
+    fn tc_multiscale_icp_point_to_point(ctx: *mut TcContext, src: *const f32, ns: u64,
+                                        tgt: *const f32, nt: u64, init: *const f32,
+                                        levels: *const TcIcpScaleLevel, n_levels: u32,
+                                        final_iters: u32, final_max_dist: f32, conv: f32,
+                                        out: *mut TcIcpResult, pairs: *mut u64) -> c_int;
+    fn tc_gicp(ctx: *mut TcContext, src: *const f32, ns: u64, tgt: *const f32, nt: u64,
+               init: *const f32, max_iters: u32, max_dist: f32, conv: f32, k: u32,
+               out: *mut TcIcpResult, pairs: *mut u64) -> c_int;
+    fn tc_cloud_len(c: *const TcCloud) -> u64;
+    fn tc_cloud_download(ctx: *mut TcContext, c: *const TcCloud, out: *mut f32) -> c_int;
+    fn tc_voxel_grid_filter(ctx: *mut TcContext, c: *const TcCloud, voxel: f32,
+                            out: *mut *mut TcCloud) -> c_int;
+    fn tc_radius_outlier_removal(ctx: *mut TcContext, c: *const TcCloud, radius: f32,
+                                 min_neighbors: u32, out: *mut *mut TcCloud) -> c_int;
+    fn tc_statistical_outlier_removal(ctx: *mut TcContext, c: *const TcCloud, k: u32, value: f32,
+                                      mode: c_int, stats: *mut f32, out: *mut *mut TcCloud) -> c_int;
 }
+
+/// `IcpScaleLevel` (registration.rs:28-35) as it crosses the ABI; negative distance = None.
+#[repr(C)]
+pub struct TcIcpScaleLevel { pub voxel_size: f32, pub max_iterations: u32, pub max_correspondence_distance: f32 }
 
 /// One context per thread (the C ABI serialises calls on a context's stream).
 pub struct Context(*mut TcContext);
@@ -159,6 +182,104 @@ pub fn icp_point_to_plane_detailed(source: &[Point3f], target: &[Point3f], norma
     Ok(IcpOut { transformation: iso, mse: res.mse, iterations: res.iterations as usize,
                 converged: res.converged != 0,
                 correspondences: (0..m).map(|i| (pairs[2 * i] as usize, pairs[2 * i + 1] as usize)).collect() })
+}
+
+fn iso7(init: &Isometry3<f32>) -> [f32; 7] {
+    let q = init.rotation.quaternion().coords;
+    let t = init.translation.vector;
+    [t.x, t.y, t.z, q[0], q[1], q[2], q[3]]
+}
+
+fn icp_out(res: &TcIcpResult, pairs: &[u64]) -> IcpOut {
+    let r = res.transform;
+    let m = res.n_correspondences as usize;
+    IcpOut {
+        transformation: Isometry3::from_parts(
+            Translation3::new(r[0], r[1], r[2]),
+            UnitQuaternion::new_unchecked(Quaternion::new(r[6], r[3], r[4], r[5]))),
+        mse: res.mse, iterations: res.iterations as usize, converged: res.converged != 0,
+        correspondences: (0..m).map(|i| (pairs[2 * i] as usize, pairs[2 * i + 1] as usize)).collect(),
+    }
+}
+
+/// Drop-in for `icp_detailed` / `icp_point_to_point` (registration.rs:258, 644).
+pub fn icp_point_to_point(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>,
+                          max_iters: usize, conv: f32, max_dist: Option<f32>) -> Result<IcpOut> {
+    let init7 = iso7(&init);
+    let mut res = TcIcpResult::default();
+    let mut pairs = vec![0u64; 2 * source.len().max(1)];
+    CTX.with(|c| c.check(unsafe {
+        tc_icp_point_to_point(c.0, source.as_ptr() as *const f32, source.len() as u64,
+                              target.as_ptr() as *const f32, target.len() as u64, init7.as_ptr(),
+                              max_iters as u32, max_dist.unwrap_or(-1.0), conv, &mut res, pairs.as_mut_ptr())
+    }))?;
+    Ok(icp_out(&res, &pairs))
+}
+
+/// Drop-in for `multiscale_icp_point_to_point` (registration.rs:704).
+pub fn multiscale_icp_point_to_point(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>,
+                                     levels: &[(f32, usize, Option<f32>)], final_iters: usize,
+                                     final_max_dist: Option<f32>, conv: f32) -> Result<IcpOut> {
+    let lv: Vec<TcIcpScaleLevel> = levels.iter().map(|&(v, it, d)| TcIcpScaleLevel {
+        voxel_size: v, max_iterations: it as u32, max_correspondence_distance: d.unwrap_or(-1.0) }).collect();
+    let init7 = iso7(&init);
+    let mut res = TcIcpResult::default();
+    let mut pairs = vec![0u64; 2 * source.len().max(1)];
+    CTX.with(|c| c.check(unsafe {
+        tc_multiscale_icp_point_to_point(c.0, source.as_ptr() as *const f32, source.len() as u64,
+                                         target.as_ptr() as *const f32, target.len() as u64,
+                                         init7.as_ptr(), lv.as_ptr(), lv.len() as u32, final_iters as u32,
+                                         final_max_dist.unwrap_or(-1.0), conv, &mut res, pairs.as_mut_ptr())
+    }))?;
+    Ok(icp_out(&res, &pairs))
+}
+
+/// Drop-in for `gicp` (gicp.rs:117); arguments are the fields of `GicpConfig`.
+pub fn gicp(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>, max_iters: usize,
+            max_dist: f32, conv: f32, k: usize) -> Result<IcpOut> {
+    let init7 = iso7(&init);
+    let mut res = TcIcpResult::default();
+    let mut pairs = vec![0u64; 2 * source.len().max(1)];
+    CTX.with(|c| c.check(unsafe {
+        tc_gicp(c.0, source.as_ptr() as *const f32, source.len() as u64, target.as_ptr() as *const f32,
+                target.len() as u64, init7.as_ptr(), max_iters as u32, max_dist, conv, k as u32,
+                &mut res, pairs.as_mut_ptr())
+    }))?;
+    Ok(icp_out(&res, &pairs))
+}
+
+/// Shared tail of the three filters: upload, run `f`, download the resulting cloud.
+fn filter_with(points: &[Point3f],
+               f: impl Fn(*mut TcContext, *const TcCloud, *mut *mut TcCloud) -> c_int) -> Result<Vec<Point3f>> {
+    CTX.with(|c| {
+        let (mut cloud, mut out) = (ptr::null_mut(), ptr::null_mut());
+        c.check(unsafe { tc_cloud_upload(c.0, points.as_ptr() as *const f32, points.len() as u64, &mut cloud) })?;
+        let st = f(c.0, cloud, &mut out);
+        unsafe { tc_cloud_free(cloud) };
+        c.check(st)?;
+        let n = unsafe { tc_cloud_len(out) } as usize;
+        let mut v = vec![Point3f::origin(); n];
+        let st = unsafe { tc_cloud_download(c.0, out, v.as_mut_ptr() as *mut f32) };
+        unsafe { tc_cloud_free(out) };
+        c.check(st)?;
+        Ok(v)
+    })
+}
+
+/// Drop-ins for filtering.rs:38, 167, 253, 335.
+pub fn voxel_grid_filter(points: &[Point3f], voxel_size: f32) -> Result<Vec<Point3f>> {
+    filter_with(points, |ctx, c, out| unsafe { tc_voxel_grid_filter(ctx, c, voxel_size, out) })
+}
+pub fn radius_outlier_removal(points: &[Point3f], radius: f32, min_neighbors: usize) -> Result<Vec<Point3f>> {
+    filter_with(points, |ctx, c, out| unsafe { tc_radius_outlier_removal(ctx, c, radius, min_neighbors as u32, out) })
+}
+pub fn statistical_outlier_removal(points: &[Point3f], k: usize, std_dev_multiplier: f32) -> Result<Vec<Point3f>> {
+    filter_with(points, |ctx, c, out| unsafe {
+        tc_statistical_outlier_removal(ctx, c, k as u32, std_dev_multiplier, 0, ptr::null_mut(), out) })
+}
+pub fn statistical_outlier_removal_with_threshold(points: &[Point3f], k: usize, threshold: f32) -> Result<Vec<Point3f>> {
+    filter_with(points, |ctx, c, out| unsafe {
+        tc_statistical_outlier_removal(ctx, c, k as u32, threshold, 2, ptr::null_mut(), out) })
 }
 
 #[allow(dead_code)]
