@@ -329,6 +329,11 @@ def main():
                                   peak_gbs, flush_l2, ev, dist if world > 1 else None))
         except Exception as e:
             extra["c3_error"] = repr(e)
+        if rank == 0:  # single-GPU rows of SURVEY §8(f): filters, multiscale ICP, GICP
+            try:
+                extra.update(bench_next_rows(tc, synth, ctx, ext, flush_l2, ev))
+            except Exception as e:
+                extra["next_rows_error"] = repr(e)
     line["extra"] = extra
 
     if rank == 0:
@@ -439,6 +444,58 @@ def bench_c3(args, tc, synth, ctx, ext, rank, world, barrier, max_over_ranks, pe
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                      "frac": ach / peak_gbs, "kernel": "k_icp_correspond (+ k_icp_solve)",
                      "note": "36 MB/iter working set is L2-resident; issue/latency-bound"}}}
+
+
+def bench_next_rows(tc, synth, ctx, ext, flush_l2, ev):
+    """Filters on the C2 frame (device-resident in and out) and the two other registrations on a
+    200k terrain pair (host arrays through the C ABI, uploads included)."""
+    def timed(fn, reps=5, warm=2):
+        ts = []
+        for it in range(warm + reps):
+            flush_l2()
+            e0, e1 = ev(), ev()
+            e0.record(ext)
+            r = fn()
+            e1.record(ext)
+            ctx.synchronize()
+            if it >= warm:
+                ts.append(e0.elapsed_time(e1))
+            if isinstance(r, tc.DeviceCloud):
+                r.free()
+        return float(np.median(ts))
+
+    pts = synth.kitti_frame()
+    n = len(pts)
+    cloud = tc.DeviceCloud(pts, ctx)
+    out = {}
+    ms = timed(lambda: tc.voxel_grid_filter(cloud, 0.2))
+    out["voxel_grid_filter_0.2m"] = {"points": n, "ms": ms, "points_per_s": n / (ms * 1e-3)}
+    ms = timed(lambda: tc.radius_outlier_removal(cloud, 0.5, 5))
+    out["radius_outlier_removal_r0.5_min5"] = {"points": n, "ms": ms, "points_per_s": n / (ms * 1e-3)}
+    ms = timed(lambda: tc.statistical_outlier_removal(cloud, 16, 1.0))
+    out["statistical_outlier_removal_k16_exact"] = {"points": n, "ms": ms, "points_per_s": n / (ms * 1e-3)}
+    ms = timed(lambda: tc.statistical_outlier_removal(cloud, 16, 1.0, fast=True))
+    out["statistical_outlier_removal_k16_fast"] = {"points": n, "ms": ms, "points_per_s": n / (ms * 1e-3)}
+    cloud.free()
+    src, tgt, _, _ = synth.scan_pair(200_000, half_extent=22.0)
+    r = [None]
+
+    def run_gicp():
+        r[0] = tc.gicp(src, tgt, tc.IDENTITY, tc.GicpConfig(max_iterations=20), ctx,
+                       want_correspondences=False)
+    ms = timed(run_gicp, reps=3, warm=1)
+    out["gicp_200k_k20"] = {"ms": ms, "iterations": r[0].iterations,
+                            "ms_per_iteration_incl_covariances": ms / max(r[0].iterations, 1)}
+
+    def run_ms():
+        r[0] = tc.multiscale_icp_point_to_point(
+            src, tgt, tc.IDENTITY, tc.MultiScaleIcpConfig(
+                levels=[tc.IcpScaleLevel(1.0, 10, 2.0), tc.IcpScaleLevel(0.5, 10, 1.0),
+                        tc.IcpScaleLevel(0.25, 15, 0.6)], final_max_correspondence_distance=0.4),
+            ctx, want_correspondences=False)
+    ms = timed(run_ms, reps=3, warm=1)
+    out["multiscale_icp_200k_3_levels"] = {"ms": ms, "iterations": r[0].iterations}
+    return {"next_rows": out}
 
 
 if __name__ == "__main__":

@@ -91,7 +91,7 @@ int tc_radius_outlier_removal(tc_context* ctx, const tc_cloud* cloud, float radi
  * neighbour with the point's own coordinates skipped, f32 sum in ascending-distance order) is
  * <= threshold.
  *   mode 0: threshold = mean + value * std_dev of those mean distances, accumulated like the
- *           reference (sequential f32 sums over the cloud) - bit-exact, ~2 ns/point serial tail;
+ *           reference (sequential f32 sums over the cloud) - bit-exact, ~6 ns/point serial tail;
  *   mode 1: same statistics from f64 tree sums (fast; a point whose mean distance lies within the
  *           reference's own f32 accumulation error of the threshold may be classified differently);
  *   mode 2: `value` IS the threshold (statistical_outlier_removal_with_threshold).

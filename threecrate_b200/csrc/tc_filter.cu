@@ -230,33 +230,48 @@ __global__ void __launch_bounds__(kThreads) k_sor_mean(const float* __restrict__
 
 // Global mean and variance of mean[] in the reference's arithmetic: SEQUENTIAL f32 sums over the
 // cloud (filtering.rs:304-312).  A float sum is not associative, so the only bit-exact way is
-// to add in the same order: one warp streams the array (coalesced loads, shuffle broadcast) and
-// every lane performs the same dependent chain of adds.  ~2 ns per point; `fast` mode below
-// replaces it with an f64 tree reduction.
-__global__ void k_sor_stats_sequential(const float* __restrict__ mean, uint32_t n,
-                                       float std_mult, float* __restrict__ out /*mean, std, thr*/) {
-  const int lane = threadIdx.x;
+// to add in the same order: the block stages 4096 values at a time in shared memory (coalesced)
+// and one thread runs the dependent chain of adds over them (~4 cycles per point per pass);
+// `fast` mode below replaces it with an f64 tree reduction.
+constexpr int kSeqChunk = 4096;
+__global__ void __launch_bounds__(256) k_sor_stats_sequential(const float* __restrict__ mean,
+                                                              uint32_t n, float std_mult,
+                                                              float* __restrict__ out /*mean, std, thr*/) {
+  __shared__ float buf[kSeqChunk];
+  __shared__ float s_gm;
   float s = 0.0f;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const float v = (base + lane < n) ? mean[base + lane] : 0.0f;
-    const int m = min(32u, n - base);
-    for (int j = 0; j < m; ++j) s = xadd(s, __shfl_sync(0xffffffffu, v, j));
-  }
-  const float gm = xdiv(s, (float)n);
-  float q = 0.0f;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const float v = (base + lane < n) ? mean[base + lane] : 0.0f;
-    const int m = min(32u, n - base);
-    for (int j = 0; j < m; ++j) {
-      const float d = xsub(__shfl_sync(0xffffffffu, v, j), gm);
-      q = xadd(q, xmul(d, d));  // powi(2) = d * d
+  for (int pass = 0; pass < 2; ++pass) {
+    const float gm = pass ? s_gm : 0.0f;
+    s = 0.0f;
+    for (uint32_t base = 0; base < n; base += kSeqChunk) {
+      const uint32_t m = min((uint32_t)kSeqChunk, n - base);
+      for (uint32_t t = threadIdx.x; t < m; t += blockDim.x) {
+        const float v = mean[base + t];
+        const float d = xsub(v, gm);
+        buf[t] = pass ? xmul(d, d) : v;  // powi(2) = d * d
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (; t + 16 <= m; t += 16) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) s = xadd(s, buf[t + u]);
+        }
+        for (; t < m; ++t) s = xadd(s, buf[t]);
+      }
+      __syncthreads();
     }
-  }
-  const float sd = xsqrt(xdiv(q, (float)n));
-  if (lane == 0) {
-    out[0] = gm;
-    out[1] = sd;
-    out[2] = xadd(gm, xmul(std_mult, sd));
+    if (threadIdx.x == 0) {
+      if (pass == 0) {
+        s_gm = xdiv(s, (float)n);
+      } else {
+        const float sd = xsqrt(xdiv(s, (float)n));
+        out[0] = s_gm;
+        out[1] = sd;
+        out[2] = xadd(s_gm, xmul(std_mult, sd));
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -451,7 +466,7 @@ extern "C" int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* c
     k_sor_mean<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, n, k1, d_idx, d_dist, d_mean);
     ctx->launches++;
     if (mode == 0) {
-      k_sor_stats_sequential<<<1, 32, 0, ctx->stream>>>(d_mean, n, value, d_stats);
+      k_sor_stats_sequential<<<1, 256, 0, ctx->stream>>>(d_mean, n, value, d_stats);
       ctx->launches++;
     } else if (mode == 1) {
       cudaMemsetAsync(d_acc, 0, 2 * sizeof(double), ctx->stream);
