@@ -218,8 +218,11 @@ def main():
             record.append((e0, e1, e2))
         return index
 
+    # one nvidia-smi poller per JOB (rank 0's GPU): eight of them polling the driver every 20 ms
+    # measurably slow every rank's launches
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         flush_l2()
         step_resident().free()
@@ -242,6 +245,11 @@ def main():
     ms_step = [a.elapsed_time(c) for a, _, c in evs]
     total_ms = max_over_ranks(float(np.sum(ms_step)))
     value = n * world * args.steps / (total_ms * 1e-3)
+    per_rank_ms = [float(np.sum(ms_step)) / args.steps]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank_ms[0])
+        per_rank_ms = [float(x) for x in gathered]
 
     # e2e: host buffers through the drop-in C-ABI call, copies inside the timed region
     lib = ctx.lib
@@ -283,7 +291,8 @@ def main():
         "config": {"workload": "C2: estimate_normals k=16 on a 120000-pt KITTI-shaped LiDAR frame "
                                "(index build + fused normals kernel), one frame per rank per step",
                    "k": K_C2, "points_per_rank": n, "l2": "flushed (256 MiB write) before every step",
-                   "timed": "CUDA events on the library stream, summed over steps, max over ranks"},
+                   "timed": "CUDA events on the library stream, summed over steps, max over ranks",
+                   "ms_per_step_by_rank": [round(x, 5) for x in per_rank_ms]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 12 * world),
                 "d2h_bytes_per_step": int(n * 24 * world), "ms_per_step": e2e_total / args.steps},
@@ -295,7 +304,7 @@ def main():
     cloud.free()
 
     # -------------------------------------------------------------------------- cpu_baseline
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline is an N=1 figure
         try:
             import oracle
 
