@@ -96,7 +96,7 @@ int tc_radius_outlier_removal(tc_context* ctx, const tc_cloud* cloud, float radi
  *           reference's own f32 accumulation error of the threshold may be classified differently);
  *   mode 2: `value` IS the threshold (statistical_outlier_removal_with_threshold).
  * stats_out (may be NULL) receives {global mean, std dev, threshold}.  k_neighbors == 0 or
- * value <= 0 -> TC_INVALID_DATA; k_neighbors > 63 is not supported by the device top-k. */
+ * value <= 0 -> TC_INVALID_DATA. */
 int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* cloud, uint32_t k_neighbors,
                                    float value, int mode, float* stats_out, tc_cloud** out);
 

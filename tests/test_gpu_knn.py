@@ -166,3 +166,25 @@ def test_kitti_strided_upload_matches_packed():
     a = tc.GridIndex(tc.DeviceCloud(raw, stride_bytes=16), k_hint=16).estimate_normals(16)
     b = tc.estimate_normals(np.ascontiguousarray(raw[:, :3]), 16)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("k", [65, 100, 257])
+def test_large_k_heap_path(orc, k):
+    """k beyond the 64-entry register lists: global-memory heap kernels, same exact result."""
+    pts = synth.kitti_frame(seed=9)[::40][:3000].copy()
+    rng = np.random.default_rng(1)
+    q = (pts[rng.integers(0, len(pts), 200)] + rng.normal(0, 0.2, (200, 3))).astype(np.float32)
+    tree = tc.KdTree(pts, k_hint=k)
+    idx, dist, cnt = tree.knn(q, k)
+    ref_idx, ref_d2 = orc.brute_knn(pts, q, k)
+    exact, modulo, mismatch = knn_parity(idx, dist, ref_idx, ref_d2, pts, q)
+    assert not mismatch and exact + modulo == len(q)
+    assert np.array_equal(dist, np.sqrt(ref_d2))
+    assert np.all(cnt == k)
+    # self-query with exclusion and k > N - 1: every other point, padded
+    small = pts[:70]
+    sidx, sdist, scnt = tc.k_nearest_neighbors(small, k)
+    m = min(k, 69)
+    assert np.all(scnt == m) and np.all(sidx[:, m:] == 0xFFFFFFFF)
+    ridx, rdist, rcnt = orc.k_nearest_neighbors(small, k)
+    assert np.array_equal(sdist[:, :m], rdist[:, :m])

@@ -177,3 +177,9 @@ def test_multilevel_index_on_skewed_cloud_is_exact(orc):
     bi, bd2 = orc.brute_knn(pts, pts[sel], 16)
     assert np.array_equal(idx.astype(np.uint64), bi)
     assert np.array_equal(dist, np.sqrt(bd2))
+
+
+def test_large_k_normals(orc):
+    """k + 1 > 64 runs on the global-memory heap kernels."""
+    pts = synth.terrain(6000, 4.0, seed=12, noise=0.004, wall_fraction=0.1)
+    _parity(orc, pts, 80, label="terrain k=80 (heap path)")

@@ -658,8 +658,6 @@ extern "C" int tc_gicp(tc_context* ctx, const float* src_aos, uint64_t ns, const
                        " points for reliable covariance estimation (k_correspondences=" +
                        std::to_string(k_correspondences) + "); got source=" + std::to_string(ns) +
                        ", target=" + std::to_string(nt));
-  if (min_k > 64)
-    return tc_fail(ctx, TC_INVALID_DATA, "GICP: k_correspondences > 64 exceeds the device top-k");
   if (!src_aos || !tgt_aos || !init || !out) return TC_INVALID_DATA;
   tc_cloud *src = nullptr, *tgt = nullptr;
   tc_index* ix = nullptr;

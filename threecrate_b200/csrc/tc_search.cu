@@ -546,6 +546,114 @@ k_radius_search(LevelSet ls, int level, float qx, float qy, float qz, float radi
   }
 }
 
+// ---------------------------------------------------------------------------------- any k
+// k + 1 beyond the register lists (> 64): a binary max-heap of u64 (d2, index) keys per query in
+// global memory (the query's `need` slots are contiguous, so the hot top of the heap stays in
+// L1), the same exact ring search, then an in-place heapsort -> ascending (d2, index).
+struct HeapK {
+  uint64_t* h;
+  uint32_t cap, n;
+  __device__ __forceinline__ void init() { n = 0; }
+  __device__ __forceinline__ bool full() const { return n == cap; }
+  __device__ __forceinline__ float kth() const {
+    return n == cap ? __uint_as_float((uint32_t)(h[0] >> 32)) : INFINITY;
+  }
+  __device__ __forceinline__ void sift_down(uint32_t i, uint32_t end, uint64_t v) {
+    while (true) {
+      uint32_t c = 2 * i + 1;
+      if (c >= end) break;
+      if (c + 1 < end && h[c + 1] > h[c]) ++c;
+      if (h[c] <= v) break;
+      h[i] = h[c];
+      i = c;
+    }
+    h[i] = v;
+  }
+  __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
+                                       float qx, float qy, float qz, int) {
+    for (uint32_t j = lo; j < hi; ++j) {
+      const float4 c = __ldg(&pts[j]);
+      const float d2 = dist2_exact(c.x, c.y, c.z, qx, qy, qz);
+      const uint64_t key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+      if (n < cap) {  // sift up
+        uint32_t i = n++;
+        while (i > 0) {
+          const uint32_t p = (i - 1) >> 1;
+          if (h[p] >= key) break;
+          h[i] = h[p];
+          i = p;
+        }
+        h[i] = key;
+      } else if (key < h[0]) {
+        sift_down(0, cap, key);
+      }
+    }
+  }
+  __device__ __forceinline__ void sort_ascending() {
+    for (uint32_t end = n; end > 1; --end) {
+      const uint64_t last = h[end - 1];
+      h[end - 1] = h[0];
+      sift_down(0, end - 1, last);
+    }
+  }
+};
+struct GlobalKeys {
+  const uint64_t* key;
+  int n;
+  const float* __restrict__ xyz;
+  static constexpr int kCount = 1;
+  static constexpr bool kUnroll = false;
+  __device__ __forceinline__ int count() const { return n; }
+  __device__ __forceinline__ Nb head(int i) const {
+    Nb r;
+    r.valid = true;
+    r.id = (uint32_t)key[i];
+    r.d2 = __uint_as_float((uint32_t)(key[i] >> 32));
+    r.x = r.y = r.z = 0.0f;
+    return r;
+  }
+  __device__ __forceinline__ void coords(Nb& r) const {
+    const float* p = xyz + 3 * (uint64_t)r.id;
+    r.x = __ldg(p + 0);
+    r.y = __ldg(p + 1);
+    r.z = __ldg(p + 2);
+  }
+};
+
+__global__ void __launch_bounds__(kBlock)
+k_knn_big(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end,
+          uint32_t k, uint32_t need, int drop_self, uint32_t* __restrict__ idx_out,
+          float* __restrict__ dist_out, uint32_t* __restrict__ count_out,
+          uint64_t* __restrict__ heaps) {
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+  if (t >= q_end - q_begin) return;
+  const float4 q = __ldg(&queries[q_begin + t]);
+  HeapK hk{heaps + (uint64_t)t * need, need, 0};
+  int level;
+  level_search(ls, q.x, q.y, q.z, need, hk, level);
+  hk.sort_ascending();
+  knn_emit(GlobalKeys{hk.h, (int)hk.n, nullptr}, __float_as_uint(q.w), k, drop_self, idx_out,
+           dist_out, count_out);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_normals_big(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end,
+              uint32_t own_begin, uint32_t own_end, uint32_t k, int orient, float vpx, float vpy,
+              float vpz, float* __restrict__ out, uint64_t* __restrict__ heaps) {
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+  if (t >= q_end - q_begin) return;
+  const float4 q = __ldg(&ls.pts[0][q_begin + t]);
+  if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
+  HeapK hk{heaps + (uint64_t)t * (k + 1), k + 1, 0};
+  int level;
+  level_search(ls, q.x, q.y, q.z, k + 1, hk, level);
+  hk.sort_ascending();
+  normals_emit(GlobalKeys{hk.h, (int)hk.n, xyz}, q, __float_as_uint(q.w), k, orient, vpx, vpy, vpz,
+               out);
+}
+
+constexpr uint32_t kBigChunk = 1u << 18;  // queries per launch of the any-k kernels (heap memory)
+
 // smallest instantiated list size >= need (0 if unsupported)
 constexpr int kSizes[] = {1, 2, 4, 6, 8, 11, 13, 17, 21, 25, 31, 33, 40, 48, 64};
 inline int pick_size(uint32_t need) {
@@ -599,8 +707,6 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   const int drop_self = (exclude_self && self_query) ? 1 : 0;
   const uint32_t need = k + (drop_self ? 1u : 0u);
   const int sz = pick_size(need);
-  if (sz == 0)
-    return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 64 incl. self)");
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
   int flags = g_tc_search_flags;
@@ -608,6 +714,21 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   if (two_pass) flags |= 2;  // pruning is always worth it with the batch scan
   const LevelSet ls = ix->level_set(flags);
   if (self_query) d_queries_sorted = ix->lv[0].d_pts;
+  if (sz == 0) {  // beyond the register lists: global-memory heaps, a chunk of queries at a time
+    const uint32_t chunk = std::min(nq, kBigChunk);
+    uint64_t* d_heaps = nullptr;
+    TC_TRY(tc_alloc(ctx, &d_heaps, (uint64_t)chunk * need));
+    for (uint64_t b = q_begin; b < q_end; b += chunk) {
+      const uint64_t e = std::min<uint64_t>(q_end, b + chunk);
+      k_knn_big<<<(uint32_t)((e - b + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(
+          ls, d_queries_sorted, (uint32_t)b, (uint32_t)e, k, need, drop_self, d_idx_out,
+          d_dist_out, d_count_out, d_heaps);
+      ctx->launches++;
+    }
+    tc_free(ctx, d_heaps);
+    TC_CUDA(ctx, cudaGetLastError());
+    return TC_OK;
+  }
   if (!two_pass) {
     TC_DISPATCH_K(sz, (k_knn<KK><<<grid, kBlock, 0, ctx->stream>>>(
                           ls, d_queries_sorted, (uint32_t)q_begin, (uint32_t)q_end, k, need,
@@ -645,8 +766,6 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
                        const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos) {
   if (q_end <= q_begin) return TC_OK;
   const int sz = pick_size(k + 1);
-  if (sz == 0)
-    return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 63 for normals)");
   const bool whole = (q_begin == 0 && q_end >= ix->n);
   const uint32_t own_begin = (uint32_t)q_begin;
   const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
@@ -657,6 +776,21 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const bool two_pass = two_pass_shape(k + 1, flags) != 0;
   if (two_pass) flags |= 2;
   const LevelSet ls = ix->level_set(flags);
+  if (sz == 0) {  // k + 1 > 64: global-memory heaps, a chunk of queries at a time
+    const uint32_t chunk = std::min(nq, kBigChunk);
+    uint64_t* d_heaps = nullptr;
+    TC_TRY(tc_alloc(ctx, &d_heaps, (uint64_t)chunk * (k + 1)));
+    for (uint64_t b = q_begin; b < q_end; b += chunk) {
+      const uint64_t e = std::min<uint64_t>(q_end, b + chunk);
+      k_normals_big<<<(uint32_t)((e - b + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(
+          ls, ix->cloud->d_xyz, (uint32_t)b, (uint32_t)e, own_begin, own_end, k, orient, vp[0],
+          vp[1], vp[2], d_out_aos, d_heaps);
+      ctx->launches++;
+    }
+    tc_free(ctx, d_heaps);
+    TC_CUDA(ctx, cudaGetLastError());
+    return TC_OK;
+  }
   if (!two_pass) {
     TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
                           ls, ix->cloud->d_xyz, (uint32_t)q_begin, (uint32_t)q_end, own_begin,
