@@ -731,7 +731,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   const uint32_t nt = (uint32_t)tgt->n;
   if (mode == kPoint && nt >= (1u << 30))
     return tc_fail(ctx, TC_INVALID_DATA, "point-to-point ICP supports targets below 2^30 points");
-  const int n_sums = mode == kPlane ? kNumSums : kNumSumsP2P;
+  const int n_sums = mode == kPoint ? kNumSumsP2P : kNumSums;
 
   // sort the source spatially (own bbox, target-sized cells) so warps walk coherent target cells
   float4* d_src = nullptr;
