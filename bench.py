@@ -110,12 +110,14 @@ def run_reference(args, rank: int, world: int):
     oracle.build()
     pts = synth.kitti_frame()
     n = pts.shape[0]
-    threads = oracle.max_threads()
+    # every host core this process may use (torchrun pins OMP_NUM_THREADS=1; the thread count is
+    # passed explicitly, and under torchrun rank 0 alone runs this arm)
+    threads = max(len(os.sched_getaffinity(0)), oracle.max_threads())
     for _ in range(max(args.warmup, 1)):
-        oracle.estimate_normals(pts, K_C2)
+        oracle.estimate_normals(pts, K_C2, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.estimate_normals(pts, K_C2)
+        oracle.estimate_normals(pts, K_C2, threads=threads)
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     line = {
@@ -309,12 +311,12 @@ def main():
             import oracle
 
             oracle.build()
-            threads = oracle.max_threads()
-            oracle.estimate_normals(pts, K_C2)
+            threads = max(len(os.sched_getaffinity(0)), oracle.max_threads())
+            oracle.estimate_normals(pts, K_C2, threads=threads)
             t0 = time.perf_counter()
             reps = 0
             while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 200):
-                oracle.estimate_normals(pts, K_C2)
+                oracle.estimate_normals(pts, K_C2, threads=threads)
                 reps += 1
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n * reps / dt, "unit": UNIT, "cores": threads,
