@@ -56,7 +56,8 @@ __global__ void k_scratch_init(uint32_t* s) {
 }
 
 __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz, uint64_t n,
-                                                   uint32_t* __restrict__ s) {
+                                                   uint32_t* __restrict__ s,
+                                                   volatile uint32_t* host, uint32_t seq) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   uint32_t bad = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -91,8 +92,12 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz
     __threadfence();
     if (atomicAdd(&s[7], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
       __threadfence();
-      for (int j = 0; j < 7; ++j) s[16 + j] = atomicExch(&s[j], j < 3 ? 0xFFFFFFFFu : 0u);
+      // results go straight into the context's pinned host words (zero-copy), then the
+      // sequence number the host is spinning on: no memcpy call, no stream synchronisation
+      for (int j = 0; j < 7; ++j) host[j] = atomicExch(&s[j], j < 3 ? 0xFFFFFFFFu : 0u);
       s[7] = 0u;
+      __threadfence_system();
+      host[7] = seq;
     }
   }
 }
@@ -152,7 +157,8 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
 // (how much of the cloud is too sparse for this cell size) -> published at s[24..29]
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
                                                          uint64_t n_cells, uint32_t low_thr,
-                                                         uint32_t* __restrict__ s) {
+                                                         uint32_t* __restrict__ s,
+                                                         volatile uint32_t* host, uint32_t seq) {
   uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
        i += (uint64_t)gridDim.x * blockDim.x) {
@@ -180,8 +186,10 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
     __threadfence();
     if (atomicAdd(&s[14], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
       __threadfence();
-      for (int j = 0; j < 6; ++j) s[24 + j] = atomicExch(&s[8 + j], 0u);
+      for (int j = 0; j < 6; ++j) host[8 + j] = atomicExch(&s[8 + j], 0u);
       s[14] = 0u;
+      __threadfence_system();
+      host[15] = seq;
     }
   }
 }
@@ -265,24 +273,9 @@ struct ScanJobs {
   uint32_t tile_begin[kMaxLevels + 1];
 };
 
-// state[0] = ticket counter (as u64), state[1 + t] = (status << 32 | value) of ticket t; zeroed.
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_lookback(const __grid_constant__ ScanJobs jobs, unsigned long long* state) {
-  __shared__ uint32_t sw[kScanThreads / 32 + 1];
-  __shared__ uint32_t s_tile, s_prefix;
-  if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[0], 1ull);
-  __syncthreads();
-  const uint32_t ticket = s_tile;
-  int j = 0;
-  while (j + 1 < jobs.n && ticket >= jobs.tile_begin[j + 1]) ++j;
-  const uint32_t first = jobs.tile_begin[j];  // first ticket of this table
-  const uint32_t* in = jobs.in[j];
-  uint32_t* out = jobs.out[j];
-  const uint64_t n = jobs.len[j];
-  const uint32_t tile = ticket - first;
-  const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-  uint32_t v[kScanItems];
-  uint32_t s = 0;
+// 16 consecutive items of one thread (vector loads when aligned and fully inside the table)
+__device__ __forceinline__ uint32_t scan_load16(const uint32_t* in, uint64_t base, uint64_t n,
+                                                uint32_t (&v)[kScanItems]) {
   if (base + kScanItems <= n && (((uintptr_t)(in + base)) & 15) == 0) {
 #pragma unroll
     for (int it = 0; it < kScanItems; it += 4) {
@@ -296,10 +289,39 @@ k_scan_lookback(const __grid_constant__ ScanJobs jobs, unsigned long long* state
 #pragma unroll
     for (int it = 0; it < kScanItems; ++it) v[it] = (base + it < n) ? in[base + it] : 0u;
   }
+  uint32_t s = 0;
 #pragma unroll
   for (int it = 0; it < kScanItems; ++it) s += v[it];
+  return s;
+}
+
+// state[0] = ticket counter (as u64), state[1 + t] = (status << 32 | value) of ticket t; zeroed.
+// A tile is `sub` consecutive chunks of kScanTile items: inclusive prefixes travel at most 32
+// tiles per look-back step (~1 us each), so a multi-million-cell table is cut into a few hundred
+// large tiles rather than a thousand small ones.  Phase A sums the tile and publishes, the
+// look-back resolves the prefix, phase B re-reads the tile (L2-hot) and writes the scan.
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_lookback(const __grid_constant__ ScanJobs jobs, unsigned long long* state, int sub) {
+  __shared__ uint32_t sw[kScanThreads / 32 + 1];
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[0], 1ull);
+  __syncthreads();
+  const uint32_t ticket = s_tile;
+  int j = 0;
+  while (j + 1 < jobs.n && ticket >= jobs.tile_begin[j + 1]) ++j;
+  const uint32_t first = jobs.tile_begin[j];  // first ticket of this table
+  const uint32_t* in = jobs.in[j];
+  uint32_t* out = jobs.out[j];
+  const uint64_t n = jobs.len[j];
+  const uint32_t tile = ticket - first;
+  const uint64_t tile_base = (uint64_t)tile * kScanTile * sub;
+  uint32_t v[kScanItems];
+  // ---- phase A: tile total
+  uint32_t s = 0;
+  for (int u = 0; u < sub; ++u)
+    s += scan_load16(in, tile_base + (uint64_t)u * kScanTile + (uint64_t)threadIdx.x * kScanItems, n, v);
   uint32_t total;
-  uint32_t ex = block_exclusive_scan(s, sw, total);
+  block_exclusive_scan(s, sw, total);
   if (threadIdx.x < 32) {
     // warp-wide look-back: lane j inspects predecessor (p - j); the nearest tile that already
     // published an inclusive prefix ends the walk, the aggregates in front of it are summed
@@ -336,13 +358,21 @@ k_scan_lookback(const __grid_constant__ ScanJobs jobs, unsigned long long* state
     if (lane == 0) s_prefix = prefix;
   }
   __syncthreads();
-  ex += s_prefix;
+  // ---- phase B: scan chunk by chunk with a running prefix
+  uint32_t running = s_prefix;
+  for (int u = 0; u < sub; ++u) {
+    const uint64_t base = tile_base + (uint64_t)u * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    const uint32_t cs = scan_load16(in, base, n, v);
+    uint32_t chunk_total;
+    uint32_t ex = block_exclusive_scan(cs, sw, chunk_total) + running;
 #pragma unroll
-  for (int it = 0; it < kScanItems; ++it) {
-    const uint64_t i = base + it;
-    if (i < n) out[i] = ex;
-    ex += v[it];
-    if (i == n - 1) out[n] = ex;
+    for (int it = 0; it < kScanItems; ++it) {
+      const uint64_t i = base + it;
+      if (i < n) out[i] = ex;
+      ex += v[it];
+      if (i == n - 1) out[n] = ex;
+    }
+    running += chunk_total;
   }
 }
 
@@ -445,13 +475,27 @@ int key_bits_for(uint64_t n_cells) {
 // ==========================================================================================
 // `d_state` (tiles + 1 u64 words, zeroed) may be supplied by the caller; otherwise it is
 // allocated and cleared here.
-static int scan_tables(tc_context* ctx, ScanJobs& jobs, unsigned long long* d_state) {
+// chunks per tile such that the largest table is cut into at most ~256 tiles
+static int scan_sub(const ScanJobs& jobs) {
+  uint64_t longest = 0;
+  for (int j = 0; j < jobs.n; ++j) longest = std::max(longest, jobs.len[j]);
+  const uint64_t chunks = (longest + kScanTile - 1) / kScanTile;
+  return (int)std::min<uint64_t>(64, std::max<uint64_t>(1, (chunks + 255) / 256));
+}
+static uint32_t scan_tiles(ScanJobs& jobs, int sub) {
   uint32_t tiles = 0;
+  const uint64_t per_tile = (uint64_t)kScanTile * sub;
   for (int j = 0; j < jobs.n; ++j) {
     jobs.tile_begin[j] = tiles;
-    tiles += (uint32_t)((jobs.len[j] + kScanTile - 1) / kScanTile);
+    tiles += (uint32_t)((jobs.len[j] + per_tile - 1) / per_tile);
   }
   jobs.tile_begin[jobs.n] = tiles;
+  return tiles;
+}
+
+static int scan_tables(tc_context* ctx, ScanJobs& jobs, unsigned long long* d_state) {
+  const int sub = scan_sub(jobs);
+  const uint32_t tiles = scan_tiles(jobs, sub);
   if (tiles == 0) return TC_OK;
   unsigned long long* own = nullptr;
   if (!d_state) {
@@ -460,7 +504,7 @@ static int scan_tables(tc_context* ctx, ScanJobs& jobs, unsigned long long* d_st
                                  ctx->stream));
     d_state = own;
   }
-  k_scan_lookback<<<tiles, kScanThreads, 0, ctx->stream>>>(jobs, d_state);
+  k_scan_lookback<<<tiles, kScanThreads, 0, ctx->stream>>>(jobs, d_state, sub);
   TC_LAUNCHED(ctx);
   tc_free(ctx, own);
   return TC_OK;
@@ -519,12 +563,30 @@ int tci_scratch_arm(tc_context* ctx) {
   return TC_OK;
 }
 
+// Wait until a kernel's last block has stored `seq` into the pinned host word `flag` (its results
+// were stored before it, fenced system-wide).  Polling pinned memory costs ~2 us after the kernel
+// ends; a memcpy + cudaStreamSynchronize pair costs 10-15 us, and the index build is host-bound.
+static int wait_host_flag(tc_context* ctx, volatile uint32_t* flag, uint32_t seq) {
+  for (uint64_t spins = 0;; ++spins) {
+    if (*flag == seq) return TC_OK;
+    if ((spins & 0xFFF) == 0xFFF) {  // every few thousand polls: did the stream die or drain?
+      const cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess) {  // nothing left in flight: the flag must be there now
+        if (*flag == seq) return TC_OK;
+        return tc_fail(ctx, TC_GPU, "device result flag never arrived");
+      }
+      if (e != cudaErrorNotReady)
+        return tc_fail(ctx, TC_GPU, std::string("kernel failed: ") + cudaGetErrorString(e));
+    }
+  }
+}
+
 int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]) {
-  k_bbox<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(d_xyz, n, ctx->d_scratch);
+  const uint32_t seq = ++ctx->seq;
+  k_bbox<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(d_xyz, n, ctx->d_scratch,
+                                                                      ctx->h_scratch, seq);
   TC_LAUNCHED(ctx);
-  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch + 16, 8 * sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, ctx->stream));
-  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  TC_TRY(wait_host_flag(ctx, ctx->h_scratch + 7, seq));
   if (ctx->h_scratch[6] != 0)
     return tc_fail(ctx, TC_INVALID_DATA, "point coordinates must be finite (NaN/Inf found)");
   for (int a = 0; a < 3; ++a) {
@@ -598,12 +660,11 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   k_hist_levels<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n,
                                                                          jobs);
   TC_LAUNCHED(ctx);
+  const uint32_t seq = ++ctx->seq;
   k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
-      d_counts, n_cells, low_thr, ctx->d_scratch);
+      d_counts, n_cells, low_thr, ctx->d_scratch, ctx->h_scratch, seq);
   TC_LAUNCHED(ctx);
-  TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 24, 6 * sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, ctx->stream));
-  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  TC_TRY(wait_host_flag(ctx, ctx->h_scratch + 15, seq));
   for (int j = 0; j < 6; ++j) stats[j] = ctx->h_scratch[8 + j];
   return TC_OK;
 }

@@ -21,7 +21,9 @@ struct tc_context {
   int sm_count = 148;
   // small device scratch (bbox / stats / flags) and its pinned host mirror
   uint32_t* d_scratch = nullptr;   // 64 words
-  uint32_t* h_scratch = nullptr;   // pinned, 64 words
+  uint32_t* h_scratch = nullptr;   // pinned + device-visible (UVA), 64 words: kernels publish small
+                                   // results here and the host polls a sequence word
+  uint32_t seq = 0;                // last sequence number handed to a publishing kernel
 };
 
 struct tc_cloud {
