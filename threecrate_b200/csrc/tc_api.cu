@@ -64,6 +64,8 @@ extern "C" void tc_context_destroy(tc_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < tc_context::kWsSlots; ++i)
+    if (ctx->ws[i]) cudaFree(ctx->ws[i]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -650,7 +650,7 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
                     uint32_t** d_counts_out, uint32_t stats[6]) {
   const uint64_t n = cloud->n, n_cells = cells_of(g);
   uint32_t* d_counts = nullptr;
-  TC_TRY(tc_alloc(ctx, &d_counts, n_cells + 1));
+  TC_TRY(tc_ws_get(ctx, 0, &d_counts, n_cells + 1));
   *d_counts_out = d_counts;
   TC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
   LevelJobs jobs{};
@@ -739,7 +739,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   st = trial_histogram(ctx, cloud, g, low_thr, &d_trial, stats);
   trace.mark("trial histogram+stats");
   if (st != TC_OK) {
-    tc_free(ctx, d_trial);
+    tc_ws_release(ctx, 0, d_trial);
     delete ix;
     return st;
   }
@@ -816,7 +816,7 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   twords += 2 * (tiles + 1);
   uint32_t* d_tmp = nullptr;
   st = tc_alloc(ctx, &ix->d_arena, words);
-  if (st == TC_OK) st = tc_alloc(ctx, &d_tmp, twords);
+  if (st == TC_OK) st = tc_ws_get(ctx, 1, &d_tmp, twords);
   if (st == TC_OK &&
       cudaMemsetAsync(d_tmp, 0, twords * sizeof(uint32_t), ctx->stream) != cudaSuccess)
     st = tc_fail(ctx, TC_GPU, "memset failed");
@@ -847,8 +847,8 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
       if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "index build launch failed");
     }
   }
-  tc_free(ctx, d_tmp);
-  tc_free(ctx, d_trial);
+  tc_ws_release(ctx, 1, d_tmp);
+  tc_ws_release(ctx, 0, d_trial);
   trace.mark("levels: hist+scan+scatter");
   if (st != TC_OK) {
     tc_index_free(ix);

@@ -24,6 +24,12 @@ struct tc_context {
   uint32_t* h_scratch = nullptr;   // pinned + device-visible (UVA), 64 words: kernels publish small
                                    // results here and the host polls a sequence word
   uint32_t seq = 0;                // last sequence number handed to a publishing kernel
+  // small grow-only device workspaces reused across calls (index-build histograms, fallback
+  // lists): every allocation call costs the host 1-2 us and the LiDAR-frame path is host-bound
+  static constexpr int kWsSlots = 3;
+  static constexpr uint64_t kWsMaxBytes = 64ull << 20;  // larger requests are not cached
+  void* ws[kWsSlots] = {nullptr, nullptr, nullptr};
+  uint64_t ws_bytes[kWsSlots] = {0, 0, 0};
 };
 
 struct tc_cloud {
@@ -122,6 +128,27 @@ inline int tc_alloc(tc_context* ctx, T** p, uint64_t count) {
 }
 inline void tc_free(tc_context* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
+}
+// Workspace slot `slot`: returns a buffer of at least `count` T, cached in the context when small
+// (release with tc_ws_release, which frees only uncached buffers).  All use is stream-ordered on
+// ctx->stream and a context serves one call at a time, so reuse needs no further ordering.
+template <typename T>
+inline int tc_ws_get(tc_context* ctx, int slot, T** p, uint64_t count) {
+  const uint64_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
+  if (bytes > tc_context::kWsMaxBytes) return tc_alloc(ctx, p, count);
+  if (ctx->ws_bytes[slot] < bytes) {
+    if (ctx->ws[slot]) cudaFreeAsync(ctx->ws[slot], ctx->stream);
+    ctx->ws[slot] = nullptr;
+    ctx->ws_bytes[slot] = 0;
+    const uint64_t grown = bytes + bytes / 4;
+    TC_CUDA(ctx, cudaMallocAsync(&ctx->ws[slot], grown, ctx->stream));
+    ctx->ws_bytes[slot] = grown;
+  }
+  *p = (T*)ctx->ws[slot];
+  return TC_OK;
+}
+inline void tc_ws_release(tc_context* ctx, int slot, void* p) {
+  if (p && p != ctx->ws[slot]) cudaFreeAsync(p, ctx->stream);
 }
 
 // ------------------------------------------------------------------------------------------

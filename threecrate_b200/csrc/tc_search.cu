@@ -737,7 +737,7 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
     return TC_OK;
   }
   uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions that overflowed on ties
-  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
+  TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
 #define TC_KNN2(LL, XX)                                                                       \
   k_knn2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,   \
@@ -756,7 +756,7 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
                         ls, d_queries_sorted, 0u, 0u, k, need, drop_self, d_idx_out, d_dist_out,
                         d_count_out, d_fb + 1, d_fb)));
   TC_LAUNCHED(ctx);
-  tc_free(ctx, d_fb);
+  tc_ws_release(ctx, 2, d_fb);
   return TC_OK;
 }
 
@@ -800,7 +800,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
     return TC_OK;
   }
   uint32_t* d_fb = nullptr;
-  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)nq + 1));
+  TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
   TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
 #define TC_NORMALS2(LL, XX)                                                                  \
   k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
@@ -819,7 +819,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
                         ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],
                         d_out_aos, d_fb + 1, d_fb, nullptr)));
   TC_LAUNCHED(ctx);
-  tc_free(ctx, d_fb);
+  tc_ws_release(ctx, 2, d_fb);
   return TC_OK;
 }
 
