@@ -198,9 +198,20 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
 // every level of `jobs`.  The order INSIDE a cell is arrival order (not deterministic) — nothing
 // downstream depends on it: every selection is keyed by (d2, original index) and multi-GPU
 // shards own whole cells.
+// (`zero` lists up to two word ranges nothing in this launch reads - the scan's tile states, an
+//  abandoned trial histogram - which are cleared here so the cached workspaces are left all zero)
+struct ZeroJobs {
+  uint32_t* p[2];
+  uint64_t n[2];
+};
 __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __restrict__ xyz,
                                                              uint32_t n,
-                                                             const __grid_constant__ LevelJobs jobs) {
+                                                             const __grid_constant__ LevelJobs jobs,
+                                                             const ZeroJobs zero) {
+  for (int z = 0; z < 2; ++z)
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero.n[z];
+         i += (uint64_t)gridDim.x * blockDim.x)
+      zero.p[z][i] = 0u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float x = xyz[3 * (uint64_t)i + 0], y = xyz[3 * (uint64_t)i + 1],
                 z = xyz[3 * (uint64_t)i + 2];
@@ -650,9 +661,8 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
                     uint32_t** d_counts_out, uint32_t stats[6]) {
   const uint64_t n = cloud->n, n_cells = cells_of(g);
   uint32_t* d_counts = nullptr;
-  TC_TRY(tc_ws_get(ctx, 0, &d_counts, n_cells + 1));
+  TC_TRY(tc_ws_get_zeroed(ctx, 0, &d_counts, n_cells + 1));
   *d_counts_out = d_counts;
-  TC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
   LevelJobs jobs{};
   jobs.n = 1;
   jobs.l[0].g = g;
@@ -739,10 +749,11 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   st = trial_histogram(ctx, cloud, g, low_thr, &d_trial, stats);
   trace.mark("trial histogram+stats");
   if (st != TC_OK) {
-    tc_ws_release(ctx, 0, d_trial);
+    tc_ws_release_zeroed(ctx, 0, d_trial, false);
     delete ix;
     return st;
   }
+  const uint64_t trial_words = cells_of(g) + 1;
   bool primary_counted = true;  // d_trial holds the primary histogram
   const float pop1 = (float)n / (float)std::max(1u, stats[0]);
   if (auto_cell && !(pop1 > target * 0.7f && pop1 < target * 1.4f)) {
@@ -816,10 +827,8 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   twords += 2 * (tiles + 1);
   uint32_t* d_tmp = nullptr;
   st = tc_alloc(ctx, &ix->d_arena, words);
-  if (st == TC_OK) st = tc_ws_get(ctx, 1, &d_tmp, twords);
-  if (st == TC_OK &&
-      cudaMemsetAsync(d_tmp, 0, twords * sizeof(uint32_t), ctx->stream) != cudaSuccess)
-    st = tc_fail(ctx, TC_GPU, "memset failed");
+  if (st == TC_OK) st = tc_ws_get_zeroed(ctx, 1, &d_tmp, twords);
+  bool restored = false;
   LevelJobs all{}, todo{};
   ScanJobs scan{};
   if (st == TC_OK) {
@@ -842,13 +851,21 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     }
     st = scan_tables(ctx, scan, reinterpret_cast<unsigned long long*>(d_tmp + state_off));
     if (st == TC_OK) {
-      k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all);
+      // every histogram counts back down to zero in the scatter; the scan states and (when the
+      // cell was rescaled) the abandoned trial histogram are cleared by the same launch
+      ZeroJobs zero{};
+      zero.p[0] = d_tmp + state_off;
+      zero.n[0] = twords - state_off;
+      zero.p[1] = d_trial;
+      zero.n[1] = primary_counted ? 0 : trial_words;
+      k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all, zero);
       ctx->launches++;
       if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "index build launch failed");
+      else restored = true;
     }
   }
-  tc_ws_release(ctx, 1, d_tmp);
-  tc_ws_release(ctx, 0, d_trial);
+  tc_ws_release_zeroed(ctx, 1, d_tmp, restored);
+  tc_ws_release_zeroed(ctx, 0, d_trial, restored);
   trace.mark("levels: hist+scan+scatter");
   if (st != TC_OK) {
     tc_index_free(ix);

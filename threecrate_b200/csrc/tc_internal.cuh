@@ -30,6 +30,7 @@ struct tc_context {
   static constexpr uint64_t kWsMaxBytes = 64ull << 20;  // larger requests are not cached
   void* ws[kWsSlots] = {nullptr, nullptr, nullptr};
   uint64_t ws_bytes[kWsSlots] = {0, 0, 0};
+  bool ws_zero[kWsSlots] = {false, false, false};  // cached buffer known to be all zero
 };
 
 struct tc_cloud {
@@ -149,6 +150,26 @@ inline int tc_ws_get(tc_context* ctx, int slot, T** p, uint64_t count) {
 }
 inline void tc_ws_release(tc_context* ctx, int slot, void* p) {
   if (p && p != ctx->ws[slot]) cudaFreeAsync(p, ctx->stream);
+}
+// Zero-initialised variant: the user promises (restored = true on release) that the work it
+// enqueued leaves the buffer all zero again - histograms count back down to zero while the
+// scatter consumes them - so the next call needs no memset.  Any early exit releases with
+// restored = false and the next user clears the buffer.
+template <typename T>
+inline int tc_ws_get_zeroed(tc_context* ctx, int slot, T** p, uint64_t count) {
+  const void* before = ctx->ws[slot];
+  TC_TRY(tc_ws_get(ctx, slot, p, count));
+  const bool cached = ((void*)*p == ctx->ws[slot]);
+  if (!cached || before != ctx->ws[slot] || !ctx->ws_zero[slot]) {
+    const uint64_t bytes = cached ? ctx->ws_bytes[slot] : std::max<uint64_t>(count, 1) * sizeof(T);
+    TC_CUDA(ctx, cudaMemsetAsync(*p, 0, bytes, ctx->stream));
+  }
+  if (cached) ctx->ws_zero[slot] = false;  // in use
+  return TC_OK;
+}
+inline void tc_ws_release_zeroed(tc_context* ctx, int slot, void* p, bool restored) {
+  if (p && p == ctx->ws[slot]) ctx->ws_zero[slot] = restored;
+  tc_ws_release(ctx, slot, p);
 }
 
 // ------------------------------------------------------------------------------------------
