@@ -101,9 +101,11 @@ int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* cloud, uint3
                                    float value, int mode, float* stats_out, tc_cloud** out);
 
 /* ---- spatial index (replaces KdTree::new, nearest_neighbor.rs:37-60) ---------------------- */
-/* Builds the uniform grid: bbox -> cell keys -> hand-written LSD radix sort -> cell-range scan ->
- * sorted float4 (x,y,z,original index).  cell_size <= 0 selects it automatically from `k_hint`
- * (the k the index will mostly be queried with; 1 for ICP correspondence search). */
+/* Builds the uniform grid(s): bbox -> cell histogram -> cell-range scan -> counting-sort scatter
+ * into float4 (x,y,z,original index) sorted by cell; up to three resolutions when the density is
+ * strongly skewed (LiDAR).  cell_size <= 0 selects the cell edge automatically from `k_hint`
+ * (the k the index will mostly be queried with; 1 for ICP correspondence search); an explicit
+ * cell_size builds exactly one level.  Coordinates must be finite (TC_INVALID_DATA otherwise). */
 int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
                    tc_index** out);
 void tc_index_free(tc_index* index);

@@ -1,10 +1,17 @@
-// tc_index.cu — device-resident uniform-grid index: bbox -> cell keys -> LSD radix sort ->
-// cell-range scan -> sorted float4 points.  Replaces KdTree::new
+// tc_index.cu — device-resident multi-resolution uniform-grid index.  Replaces KdTree::new
 // (threecrate-algorithms/src/nearest_neighbor.rs:37-159), which is a serial O(N log N) quickselect.
 //
-// All kernels are HBM-bound streaming passes (coalesced loads, grid sized in multiples of the SM
-// count).  Algorithmic bytes per point: bbox 12, keys+histogram 12r+4w, radix passes
-// (8r+8w) x P with P = ceil(key_bits/8), gather 4r+12r+16w, cell-range scan 8 B/cell.
+// Build: bbox -> one measured histogram trial (+ statistics) -> histogram of every level in one
+// launch -> cell-range scan of every level in one launch (decoupled look-back) -> counting-sort
+// scatter of every level in one launch into float4 {x, y, z, bits(original index)} arrays.
+// A hand-written stable LSD radix sort (tci_radix_sort_pairs) orders external query sets, ICP
+// sources and voxel keys, where no cell table exists.
+//
+// The kernels are streaming passes (coalesced loads, grids capped at a multiple of the SM count);
+// algorithmic bytes per point: bbox 12, histogram 12r + 4w per level, scatter
+// 12r + 16w per level, cell-range scan 8 B/cell.  For a LiDAR-frame-sized cloud the build is
+// bounded by host API latency, hence the fused launches, the polled host flags and the cached,
+// self-cleaning workspaces below.
 #include <chrono>
 #include <cstdlib>
 
