@@ -63,7 +63,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_host_mirror_test(force)
     return LIB
+
+
+HOST_TEST_SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp")
+HOST_TEST_BIN = os.path.join(LIBDIR, "host_mirror_test")
+
+
+def build_host_mirror_test(force: bool = False) -> str:
+    """g++ build of the C++ host-side mirror's test program (include/threecrate_cuda.hpp over the
+    C ABI); it links the shared library and finds it next to itself at run time."""
+    hpp = os.path.join(ROOT, "include", "threecrate_cuda.hpp")
+    if not os.path.exists(HOST_TEST_SRC):
+        return ""
+    newest = max(_mtime(HOST_TEST_SRC), _mtime(hpp), _mtime(LIB))
+    if force or _mtime(HOST_TEST_BIN) < newest:
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I",
+               os.path.join(ROOT, "include"), HOST_TEST_SRC, "-L", LIBDIR, "-lthreecrate_cuda",
+               "-Wl,-rpath,$ORIGIN", "-o", HOST_TEST_BIN]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host mirror test failed to build:\n{r.stdout}\n{r.stderr}")
+    return HOST_TEST_BIN
 
 
 if __name__ == "__main__":
