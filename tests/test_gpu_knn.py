@@ -188,3 +188,33 @@ def test_large_k_heap_path(orc, k):
     assert np.all(scnt == m) and np.all(sidx[:, m:] == 0xFFFFFFFF)
     ridx, rdist, rcnt = orc.k_nearest_neighbors(small, k)
     assert np.array_equal(sdist[:, :m], rdist[:, :m])
+
+
+@pytest.mark.parametrize("case", ["identical", "collinear", "far_offset", "tiny_extent", "two_clusters"])
+def test_degenerate_geometry(orc, case):
+    """Clouds that stress the grid sizing: zero / tiny extents, huge coordinates, empty space."""
+    rng = np.random.default_rng(3)
+    if case == "identical":
+        pts = np.tile(np.float32([[1.5, -2.0, 0.25]]), (300, 1))
+    elif case == "collinear":
+        pts = np.zeros((500, 3), np.float32)
+        pts[:, 0] = np.linspace(0, 10, 500, dtype=np.float32)
+    elif case == "far_offset":
+        pts = (rng.uniform(0, 5, (2000, 3)) + [4.0e5, -3.0e5, 1.0e4]).astype(np.float32)
+    elif case == "tiny_extent":
+        pts = (rng.uniform(0, 1e-5, (1500, 3)) + [1.0, 1.0, 1.0]).astype(np.float32)
+    else:
+        a = rng.normal(0, 0.05, (800, 3))
+        b = rng.normal(0, 0.05, (800, 3)) + [5000.0, 0, 0]
+        pts = np.vstack([a, b]).astype(np.float32)
+    k = 9
+    idx, dist, cnt = tc.KdTree(pts, k_hint=k).knn(pts[::7], k)
+    ref_idx, ref_d2 = orc.brute_knn(pts, pts[::7], k)
+    exact, modulo, mismatch = knn_parity(idx, dist, ref_idx, ref_d2, pts, pts[::7])
+    assert not mismatch and exact + modulo == len(pts[::7])
+    assert np.array_equal(dist, np.sqrt(ref_d2))
+    # the pipeline on top survives the same clouds (normals are unit or the +z default)
+    nrm = tc.estimate_normals(pts, 8)
+    assert np.all(np.isfinite(nrm)) and np.allclose(np.linalg.norm(nrm[:, 3:], axis=1), 1.0, atol=1e-5)
+    vox = tc.voxel_grid_filter(pts, 0.5)
+    assert np.array_equal(vox.view(np.uint32), orc.voxel_grid_filter(pts, 0.5).view(np.uint32))
