@@ -12,6 +12,7 @@
 // 12r + 16w per level, cell-range scan 8 B/cell.  For a LiDAR-frame-sized cloud the build is
 // bounded by host API latency, hence the fused launches, the polled host flags and the cached,
 // self-cleaning workspaces below.
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 
@@ -586,11 +587,17 @@ int tci_scratch_arm(tc_context* ctx) {
 // ends; a memcpy + cudaStreamSynchronize pair costs 10-15 us, and the index build is host-bound.
 static int wait_host_flag(tc_context* ctx, volatile uint32_t* flag, uint32_t seq) {
   for (uint64_t spins = 0;; ++spins) {
-    if (*flag == seq) return TC_OK;
+    if (*flag == seq) {
+      std::atomic_thread_fence(std::memory_order_acquire);  // results are read after the flag
+      return TC_OK;
+    }
     if ((spins & 0xFFF) == 0xFFF) {  // every few thousand polls: did the stream die or drain?
       const cudaError_t e = cudaStreamQuery(ctx->stream);
       if (e == cudaSuccess) {  // nothing left in flight: the flag must be there now
-        if (*flag == seq) return TC_OK;
+        if (*flag == seq) {
+          std::atomic_thread_fence(std::memory_order_acquire);
+          return TC_OK;
+        }
         return tc_fail(ctx, TC_GPU, "device result flag never arrived");
       }
       if (e != cudaErrorNotReady)

@@ -14,7 +14,7 @@ import threecrate_b200 as tc  # noqa: E402
 from threecrate_b200 import synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["c2", "c4", "c3", "knn"])
+ap.add_argument("what", choices=["c2", "c4", "c3", "knn", "gicp", "filters"])
 ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
@@ -55,3 +55,18 @@ elif a.what == "c3":
         r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, 5, None, -1.0)
         print(index.info(), r.translation)
         index.free()
+elif a.what == "gicp":
+    n = a.n or 200_000
+    src, tgt, _, _ = synth.scan_pair(n, half_extent=50.0 * (n / 1e6) ** 0.5)
+    for _ in range(a.reps):
+        r = tc.gicp(src, tgt, tc.IDENTITY, tc.GicpConfig(max_iterations=8), ctx, want_correspondences=False)
+        print(r.iterations, r.translation)
+elif a.what == "filters":
+    pts = synth.kitti_frame()
+    cloud = tc.DeviceCloud(pts, ctx)
+    for _ in range(a.reps):
+        for f in (lambda: tc.voxel_grid_filter(cloud, 0.2), lambda: tc.radius_outlier_removal(cloud, 0.5, 5),
+                  lambda: tc.statistical_outlier_removal(cloud, 16, 1.0)):
+            out = f()
+            print(len(out))
+            out.free()
