@@ -501,55 +501,4 @@ __device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* _
     }
 }
 
-// Ball query with a shrinking bound: like box_visit, but rows are taken from the query's own row
-// outwards and every row / end cell is tested against the CURRENT bound `r2()` (the best squared
-// distance so far), so a far seed costs little once the true neighbour turns up in the first
-// rows.  Exact: a row or cell is skipped only when the conservative lower bound on its distance
-// (same bound as grid_search) strictly exceeds the current best.
-template <class R2, class F>
-__device__ __forceinline__ void ball_visit(const GridParams& g, const uint32_t* __restrict__ cell_start,
-                                           float qx, float qy, float qz, R2&& r2, F&& f) {
-  const float r0 = r2();
-  const float r = xsqrt(r0) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell) +
-                  1e-30f;
-  float ux, uy, uz, u;
-  const int cx = cell_coord(qx, g.ox, g.inv, g.nx, ux);
-  const int cy = cell_coord(qy, g.oy, g.inv, g.ny, uy);
-  const int cz = cell_coord(qz, g.oz, g.inv, g.nz, uz);
-  const int xa = cell_coord(qx - r, g.ox, g.inv, g.nx, u), xb = cell_coord(qx + r, g.ox, g.inv, g.nx, u);
-  const int ya = cell_coord(qy - r, g.oy, g.inv, g.ny, u), yb = cell_coord(qy + r, g.oy, g.inv, g.ny, u);
-  const int za = cell_coord(qz - r, g.oz, g.inv, g.nz, u), zb = cell_coord(qz + r, g.oz, g.inv, g.nz, u);
-  const float fx = ux - (float)cx, fy = uy - (float)cy, fz = uz - (float)cz;
-  const float mx = g.ex + fabsf(qx - g.ox), my = g.ey + fabsf(qy - g.oy),
-              mz = g.ez + fabsf(qz - g.oz);
-  const int Rz = max(cz - za, zb - cz), Ry = max(cy - ya, yb - cy);
-  for (int iz = 0; iz <= 2 * Rz; ++iz) {
-    const int dz = ((iz + 1) >> 1) * ((iz & 1) ? -1 : 1);
-    const int z = cz + dz;
-    if (z < za || z > zb) continue;
-    const float bz = axis_bound(row_gap(dz, fz), g.cell, mz);
-    if (bz * bz * 0.99999f > r2()) continue;
-    for (int iy = 0; iy <= 2 * Ry; ++iy) {
-      const int dy = ((iy + 1) >> 1) * ((iy & 1) ? -1 : 1);
-      const int y = cy + dy;
-      if (y < ya || y > yb) continue;
-      const float by = axis_bound(row_gap(dy, fy), g.cell, my);
-      const float byz = by * by + bz * bz;
-      const float cur = r2();
-      if (byz * 0.99999f > cur) continue;
-      int x0 = xa, x1 = xb;  // trim end cells that cannot beat the current best
-      while (x0 < cx) {
-        const float bx = axis_bound(row_gap(x0 - cx, fx), g.cell, mx);
-        if ((byz + bx * bx) * 0.99999f > cur) ++x0; else break;
-      }
-      while (x1 > cx) {
-        const float bx = axis_bound(row_gap(x1 - cx, fx), g.cell, mx);
-        if ((byz + bx * bx) * 0.99999f > cur) --x1; else break;
-      }
-      const uint32_t row = cell_id(g, 0, y, z);
-      f(__ldg(&cell_start[row + x0]), __ldg(&cell_start[row + x1 + 1]));
-    }
-  }
-}
-
 }  // namespace tcs
