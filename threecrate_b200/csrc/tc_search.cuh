@@ -472,9 +472,9 @@ __device__ __forceinline__ void grid_visit(const GridParams& g, const uint32_t* 
 // squared distance r2 of the query.  Exact by monotonicity: the f32 cell-coordinate expression
 // is non-decreasing in the coordinate, so a point with |p - q| <= r on an axis has its cell
 // coordinate within [cell(q - r), cell(q + r)] (r is inflated to absorb the rounding of the
-// square root and of q -+ r).  Used where a distance bound is already known: pass 2 of the
-// two-pass selection (r2 = the final K-th d2) and ICP correspondences seeded with the previous
-// iteration's match.  `r2` may shrink while iterating (f returns the current bound).
+// square root and of q -+ r).  Used where a distance bound is already known: ICP correspondences
+// seeded with the previous iteration's match (or a probe), radius queries, the radius outlier
+// count.  The box is fixed on entry; `f` may tighten its own acceptance test while iterating.
 template <class F>
 __device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* __restrict__ cell_start,
                                           float qx, float qy, float qz, float r2, F&& f) {
