@@ -98,6 +98,26 @@ class ClockSampler:
         return out
 
 
+def _bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (what numactl / NCCL's own
+    affinity do in a deployment): the LiDAR-frame step is bounded by launch latency and by the
+    GPU's writes into pinned host memory, both of which cross the socket interconnect otherwise."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:  # NVML enumerates in PCI order, CUDA may not: go through the bus id
+            p = torch.cuda.get_device_properties(gpu_index)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank: int, world: int):
     """The reference's own CPU path cannot run here (pure Rust, no cargo/rustc): this arm times
@@ -166,6 +186,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = _bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -200,7 +222,10 @@ def main():
         return torch.cuda.Event(enable_timing=True)
 
     # ----------------------------------------------------------------------------- C2 headline
-    pts = synth.kitti_frame(seed=0x3C0FFEE + rank)
+    # every rank takes the SAME frame: weak scaling with identical per-GPU work (frames drawn with
+    # different seeds differ by +-15 % in kernel time, which max-over-ranks would book as a
+    # scaling loss)
+    pts = synth.kitti_frame(seed=0x3C0FFEE)
     n = pts.shape[0]
     h_in = tc.pinned_empty((n, 3))
     h_in[:] = pts
@@ -291,10 +316,13 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: estimate_normals k=16 on a 120000-pt KITTI-shaped LiDAR frame "
-                               "(index build + fused normals kernel), one frame per rank per step",
+                               "(index build + fused normals kernel), one frame per rank per step (the same "
+                               "synthetic frame on every rank)",
                    "k": K_C2, "points_per_rank": n, "l2": "flushed (256 MiB write) before every step",
                    "timed": "CUDA events on the library stream, summed over steps, max over ranks",
-                   "ms_per_step_by_rank": [round(x, 5) for x in per_rank_ms]},
+                   "ms_per_step_by_rank": [round(x, 5) for x in per_rank_ms],
+                   "cpu_affinity": (f"NVML-local CPUs of the rank's GPU ({len(affinity)} cores)"
+                                    if affinity else "unchanged")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 12 * world),
                 "d2h_bytes_per_step": int(n * 24 * world), "ms_per_step": e2e_total / args.steps},
@@ -311,6 +339,7 @@ def main():
             import oracle
 
             oracle.build()
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core back
             threads = max(len(os.sched_getaffinity(0)), oracle.max_threads())
             oracle.estimate_normals(pts, K_C2, threads=threads)
             t0 = time.perf_counter()
