@@ -903,6 +903,36 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   return TC_OK;
 }
 
+// Largest population of a level-0 cell, exact (max over adjacent differences of cell_start),
+// computed on first use and cached: the sharded normals launch must cover every position of a
+// cell that starts inside its range, and the build-time figures are only estimates.
+__global__ void __launch_bounds__(kThreads) k_max_population(const uint32_t* __restrict__ cs,
+                                                             uint64_t n_cells,
+                                                             uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, cs[i + 1] - cs[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+int tci_level0_max_population(tc_context* ctx, tc_index* ix, uint32_t* out) {
+  if (ix->level0_max_pop == 0 && ix->n > 0) {
+    uint32_t* d = ctx->d_scratch + 40;  // a free scratch word
+    TC_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(uint32_t), ctx->stream));
+    const GridLevel& l0 = ix->lv[0];
+    k_max_population<<<grid_for(ctx, l0.n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
+        l0.d_cell_start, l0.n_cells, d);
+    TC_LAUNCHED(ctx);
+    TC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 40, d, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ix->level0_max_pop = ctx->h_scratch[40];
+  }
+  *out = ix->level0_max_pop;
+  return TC_OK;
+}
+
 extern "C" void tc_index_free(tc_index* ix) {
   if (!ix) return;
   tc_free(ix->ctx, ix->d_arena);  // the levels are views into the arena

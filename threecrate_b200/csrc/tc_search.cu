@@ -769,7 +769,11 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const bool whole = (q_begin == 0 && q_end >= ix->n);
   const uint32_t own_begin = (uint32_t)q_begin;
   const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
-  if (!whole) q_end = std::min<uint64_t>(ix->n, q_end + ix->lv[0].max_pop_bound);
+  if (!whole) {  // cover every position of a cell that starts inside the shard (exact bound)
+    uint32_t max_pop = 0;
+    TC_TRY(tci_level0_max_population(ctx, const_cast<tc_index*>(ix), &max_pop));
+    q_end = std::min<uint64_t>(ix->n, q_end + max_pop);
+  }
   const uint32_t nq = (uint32_t)(q_end - q_begin);
   const dim3 grid((nq + kBlock - 1) / kBlock);
   int flags = g_tc_search_flags;
