@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(kThreads) k_max_population(const uint32_t* __r
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
-int tci_level0_max_population(tc_context* ctx, tc_index* ix, uint32_t* out) {
+int tci_level0_max_population(tc_context* ctx, const tc_index* ix, uint32_t* out) {
   if (ix->level0_max_pop == 0 && ix->n > 0) {
     uint32_t* d = ctx->d_scratch + 40;  // a free scratch word
     TC_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(uint32_t), ctx->stream));

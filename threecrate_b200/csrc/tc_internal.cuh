@@ -77,7 +77,7 @@ struct tc_index {
   int primary = 0;                  // the level built for the requested / automatic cell size
   GridLevel lv[kMaxLevels];         // fine -> coarse; views into d_arena
   uint32_t* d_arena = nullptr;      // cell_start tables + sorted float4 points of every level
-  uint32_t level0_max_pop = 0;      // exact, lazily computed (tci_level0_max_population)
+  mutable uint32_t level0_max_pop = 0;  // exact, lazily computed (tci_level0_max_population)
   LevelSet level_set(int flags) const {
     LevelSet s{};
     s.n = n_levels;
@@ -188,7 +188,7 @@ int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, ui
                          uint32_t** keys_out, uint32_t** vals_out);
 int tci_exclusive_scan_u32(tc_context* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 struct tc_index;
-int tci_level0_max_population(tc_context* ctx, tc_index* ix, uint32_t* out);
+int tci_level0_max_population(tc_context* ctx, const tc_index* ix, uint32_t* out);
 
 // tc_search.cu
 extern int g_tc_search_flags;  // default search variant (tc_debug_set_search_flags)

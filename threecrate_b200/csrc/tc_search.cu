@@ -771,7 +771,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
   if (!whole) {  // cover every position of a cell that starts inside the shard (exact bound)
     uint32_t max_pop = 0;
-    TC_TRY(tci_level0_max_population(ctx, const_cast<tc_index*>(ix), &max_pop));
+    TC_TRY(tci_level0_max_population(ctx, ix, &max_pop));
     q_end = std::min<uint64_t>(ix->n, q_end + max_pop);
   }
   const uint32_t nq = (uint32_t)(q_end - q_begin);
