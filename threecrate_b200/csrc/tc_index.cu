@@ -68,15 +68,30 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz
                                                    volatile uint32_t* host, uint32_t seq) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   uint32_t bad = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float v = xyz[3 * i + a];
-      if (!isfinite(v)) bad = 1;
-      mn[a] = fminf(mn[a], v);
-      mx[a] = fmaxf(mx[a], v);
+  auto upd = [&](int a, float v) {
+    if (!isfinite(v)) bad = 1;
+    mn[a] = fminf(mn[a], v);
+    mx[a] = fmaxf(mx[a], v);
+  };
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+    // four points = 48 bytes = three aligned 128-bit loads, all in flight together
+    const float4* v4 = reinterpret_cast<const float4*>(xyz);
+    const uint64_t groups = n / 4;
+    for (uint64_t gi = tid; gi < groups; gi += stride) {
+      const float4 a = v4[3 * gi], b = v4[3 * gi + 1], c = v4[3 * gi + 2];
+      upd(0, a.x); upd(1, a.y); upd(2, a.z);
+      upd(0, a.w); upd(1, b.x); upd(2, b.y);
+      upd(0, b.z); upd(1, b.w); upd(2, c.x);
+      upd(0, c.y); upd(1, c.z); upd(2, c.w);
     }
+    done = 4 * groups;
+  }
+  for (uint64_t i = done + tid; i < n; i += stride) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) upd(a, xyz[3 * i + a]);
   }
 #pragma unroll
   for (int a = 0; a < 3; ++a)
@@ -168,14 +183,25 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
                                                          uint32_t* __restrict__ s,
                                                          volatile uint32_t* host, uint32_t seq) {
   uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0};
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t c = counts[i];
+  auto upd = [&](uint32_t c) {
     occ += (c != 0);
     mx = max(mx, c);
 #pragma unroll
     for (int j = 0; j < 4; ++j) low[j] += (c <= (low_thr << j)) ? c : 0u;  // thresholds x1,2,4,8
+  };
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(counts) & 15) == 0) {
+    const uint4* c4 = reinterpret_cast<const uint4*>(counts);
+    const uint64_t groups = n_cells / 4;
+    for (uint64_t gi = tid; gi < groups; gi += stride) {
+      const uint4 c = c4[gi];
+      upd(c.x); upd(c.y); upd(c.z); upd(c.w);
+    }
+    done = 4 * groups;
   }
+  for (uint64_t i = done + tid; i < n_cells; i += stride) upd(counts[i]);
   for (int o = 16; o > 0; o >>= 1) {
     occ += __shfl_xor_sync(0xffffffffu, occ, o);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
