@@ -38,6 +38,22 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.IcpResultC) == 48  # 7 f32 + f32 + u32 + i32 + (pad) + u64
     assert _lib.IcpResultC.n_correspondences.offset == 40
     assert C.sizeof(_lib.IndexInfoC) == 72
+    assert C.sizeof(_lib.IcpScaleLevelC) == 12  # f32 + u32 + f32
+    assert _lib.IcpScaleLevelC.max_correspondence_distance.offset == 8
+
+
+def test_cpp_header_is_warning_free_and_self_contained(tmp_path):
+    """include/threecrate_cuda.hpp compiles on its own with -Wall -Wextra -Werror -pedantic
+    (syntax only: no CUDA toolkit or library needed by a host that just binds the ABI)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "threecrate_cuda.hpp"\nint main() { return 0; }\n')
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                        "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
 
 
 def test_sass_is_sm100a_only():
