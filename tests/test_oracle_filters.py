@@ -143,3 +143,35 @@ def test_multiscale_recovers_known_transform():
                                              final_max_correspondence_distance=0.5)
     assert np.linalg.norm(r.translation - T[:3]) < 2e-2
     assert r.iterations > 15 or r.converged
+
+
+def test_sor_against_scipy_ckdtree():
+    """Independent f64 restatement with scipy: same mean distances (to f32 rounding) and the same
+    keep / drop decision everywhere except within rounding of the threshold."""
+    from scipy.spatial import cKDTree
+    pts = synth.terrain(3000, 4.0, seed=8, noise=0.01)
+    rng = np.random.default_rng(0)
+    pts = np.vstack([pts, rng.uniform(-4, 4, (30, 3)) + [0, 0, 3]]).astype(np.float32)
+    k = 10
+    _, det = oracle.statistical_outlier_removal(pts, k, 1.5, return_details=True)
+    d, _ = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k + 1)
+    mean64 = d[:, 1:].mean(axis=1)  # no duplicate points in this cloud: column 0 is the point itself
+    np.testing.assert_allclose(det["mean_distances"], mean64, rtol=2e-6)
+    thr64 = mean64.mean() + 1.5 * mean64.std()
+    assert abs(det["threshold"] - thr64) <= 1e-5 * thr64
+    clear = np.abs(mean64 - thr64) > 1e-4 * thr64
+    assert np.array_equal(det["mask"][clear], (mean64 <= thr64)[clear])
+
+
+def test_radius_outlier_against_scipy_ckdtree():
+    from scipy.spatial import cKDTree
+    pts = synth.kitti_frame(seed=2)[::40][:3000].copy()
+    r, m = 0.6, 4
+    _, keep = oracle.radius_outlier_removal(pts, r, m, return_mask=True)
+    p64 = pts.astype(np.float64)
+    tree = cKDTree(p64)
+    cnt = np.array([len(x) for x in tree.query_ball_point(p64, r)]) - 1
+    # points whose m-th neighbour sits within f32 rounding of the radius may differ
+    d, _ = tree.query(p64, m + 1)
+    clear = np.abs(d[:, m] - r) > 1e-5
+    assert np.array_equal(keep[clear], (cnt >= m)[clear])

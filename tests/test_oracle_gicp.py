@@ -120,3 +120,50 @@ def test_covariances_against_numpy():
         nb = pts[idx[i].astype(np.int64)].astype(np.float64)
         ref = np.cov(nb.T, ddof=1) + 1e-4 * np.eye(3)
         np.testing.assert_allclose(cov[i], ref, rtol=2e-3, atol=1e-6)
+
+
+def test_one_gauss_newton_step_against_independent_numpy():
+    """One GICP iteration re-derived in f64 numpy straight from the formulas (M = C_t + R C_s R^T,
+    J = [-skew(Ts) | I], H d = g, delta = Rz Ry Rx) must reproduce the oracle's first step."""
+    src, tgt, _, _ = synth.scan_pair(1500, half_extent=2.5, noise=0.004)
+    r = oracle.gicp(src, tgt, None, 1, 0.6, 1e-6, 12)
+    cs = oracle.gicp_covariances(src, 12).astype(np.float64)
+    ct = oracle.gicp_covariances(tgt, 12).astype(np.float64)
+    nn_idx, nn_d2 = oracle.brute_knn(tgt, src, 1)
+    H = np.zeros((6, 6))
+    g = np.zeros(6)
+    n_corr, mse = 0, 0.0
+    for i in range(len(src)):
+        d = float(np.sqrt(nn_d2[i, 0]))
+        if d > 0.6:
+            continue
+        j = int(nn_idx[i, 0])
+        M = ct[j] + cs[i]  # R = identity on the first iteration
+        Mi = np.linalg.inv(M)
+        s = src[i].astype(np.float64)
+        A = -np.array([[0, -s[2], s[1]], [s[2], 0, -s[0]], [-s[1], s[0], 0]])
+        J = np.hstack([A, np.eye(3)])
+        res = tgt[j].astype(np.float64) - s
+        H += J.T @ Mi @ J
+        g += J.T @ Mi @ res
+        n_corr += 1
+        mse += d * d
+    x = np.linalg.solve(H, g)
+
+    def q_axis(a, ang):
+        q = np.zeros(4)
+        q[a] = np.sin(ang / 2)
+        q[3] = np.cos(ang / 2)
+        return q
+
+    def q_mul(a, b):  # [i, j, k, w]
+        ai, aj, ak, aw = a
+        bi, bj, bk, bw = b
+        return np.array([aw * bi + ai * bw + aj * bk - ak * bj, aw * bj - ai * bk + aj * bw + ak * bi,
+                         aw * bk + ai * bj - aj * bi + ak * bw, aw * bw - ai * bi - aj * bj - ak * bk])
+
+    q = q_mul(q_mul(q_axis(2, x[2]), q_axis(1, x[1])), q_axis(0, x[0]))
+    assert len(r.correspondences) == n_corr
+    assert abs(r.mse - mse / n_corr) <= 1e-5 * (mse / n_corr)
+    np.testing.assert_allclose(r.translation, x[3:], rtol=0, atol=2e-5)
+    assert angle_to(r.rotation, q.astype(F)) <= 2e-5
