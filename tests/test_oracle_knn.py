@@ -118,3 +118,36 @@ def test_binaryheap_emulation_sorted_output(orc):
         assert np.all(np.diff(d2) >= 0)
         b, bd2 = orc.brute_knn(pts, q[None], 12)
         assert np.array_equal(d2, bd2[0])
+
+
+def test_fuzz_kdtree_distances_equal_bruteforce(orc):
+    """Property test (hypothesis): on small clouds full of duplicates and lattice ties the
+    kd-tree restatement returns the same multiset of distances as the canonical brute force, for
+    every k, and radius queries return exactly the points within the radius."""
+    from hypothesis import given, settings, strategies as st
+
+    coord = st.integers(min_value=-3, max_value=3).map(lambda v: np.float32(v) * np.float32(0.25))
+    point = st.tuples(coord, coord, coord)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(point, min_size=1, max_size=40), point, st.integers(min_value=1, max_value=45),
+           st.integers(min_value=0, max_value=6))
+    def check(pts, q, k, rq):
+        p = np.array(pts, np.float32)
+        tree = orc.OracleKdTree(p)
+        idx, dist, d2 = tree.find_k_nearest(np.array(q, np.float32), k)
+        bi, bd2 = orc.brute_knn(p, np.array([q], np.float32), min(k, len(p)))
+        assert len(idx) == min(k, len(p))
+        assert np.array_equal(np.sort(d2), np.sort(bd2[0]))
+        assert np.all(np.diff(dist) >= 0)
+        radius = np.float32(rq) * np.float32(0.25)
+        ridx, rdist = tree.find_radius_neighbors(np.array(q, np.float32), float(radius))
+        dd = p - np.array(q, np.float32)
+        ref = np.nonzero((dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2]
+                         <= radius * radius)[0]
+        if radius <= 0:  # nearest_neighbor.rs:255-257: a non-positive radius finds nothing
+            assert len(ridx) == 0
+        else:
+            assert sorted(ridx.tolist()) == ref.tolist()
+
+    check()
