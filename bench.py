@@ -125,7 +125,7 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     import oracle
-    from threecrate_b200 import synth
+    from fixtures import synth
 
     oracle.build()
     pts = synth.kitti_frame()
@@ -181,7 +181,7 @@ def main():
     import torch.distributed as dist
 
     import threecrate_b200 as tc
-    from threecrate_b200 import synth
+    from fixtures import synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")

@@ -59,6 +59,27 @@ int tc_timer_start(tc_context* ctx);
 int tc_timer_stop(tc_context* ctx, float* ms_out);
 const char* tc_version(void);
 
+/* Per-call statistics of the last search / ICP call on the context (SURVEY §5 "metrics"): off by
+ * default because collecting them costs one memset and a few atomics per call.  The search
+ * counters describe the staged-tile kNN / normals kernel; the ICP block is the per-iteration
+ * history of the last registration call (first TC_STATS_MAX_ITERS iterations). */
+#define TC_STATS_MAX_ITERS 64
+typedef struct tc_stats {
+  uint64_t queries;            /* queries of the last kNN / normals launch                      */
+  uint64_t chain_queries;      /* ... finished by the exact chain kernel (ties, unproven boxes)  */
+  uint64_t rounds;             /* warp rounds (one staged box each)                              */
+  uint64_t box_splits;         /* boxes halved because they exceeded the tile                    */
+  uint64_t retries;            /* rounds repeated with a wider box or a coarser level            */
+  uint64_t candidates_staged;  /* candidate points copied into shared memory, summed over rounds */
+  uint64_t merges;             /* selection-list merges, summed over warps                       */
+  uint32_t icp_iterations;     /* iterations recorded below                                      */
+  uint32_t reserved;
+  float icp_mse[TC_STATS_MAX_ITERS];        /* mse of each iteration (pre-update residuals)    */
+  uint64_t icp_valid[TC_STATS_MAX_ITERS];   /* accepted correspondences of each iteration       */
+} tc_stats;
+int tc_stats_enable(tc_context* ctx, int on);
+int tc_last_stats(tc_context* ctx, tc_stats* out); /* synchronises the context's stream */
+
 /* ---- device-resident cloud (replaces per-call re-pack/upload of the wgpu path) ------------ */
 /* Upload `n` points from host AoS f32 (PointCloud<Point3f>.points, point_cloud.rs:11-13). */
 int tc_cloud_upload(tc_context* ctx, const float* xyz_aos, uint64_t n, tc_cloud** out);

@@ -17,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
-from threecrate_b200 import synth  # noqa: E402
+from fixtures import synth  # noqa: E402
 
 
 def build():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import threecrate_b200 as tc
-from threecrate_b200 import synth
+from fixtures import synth
 from gpu_util import quat_angle
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import threecrate_b200 as tc
-from threecrate_b200 import synth
+from fixtures import synth
 from gpu_util import knn_parity
 
 pytestmark = pytest.mark.gpu

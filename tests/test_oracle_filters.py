@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from threecrate_b200 import synth
+from fixtures import synth
 
 
 def _cube(n, step=0.1):

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from threecrate_b200 import synth
+from fixtures import synth
 
 F = np.float32
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 from scipy.spatial import cKDTree
 
-from threecrate_b200 import synth
+from fixtures import synth
 
 
 def _canon(idx, d2):

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from threecrate_b200 import synth
+from fixtures import synth
 
 
 def test_simple_plane(orc):

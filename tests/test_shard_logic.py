@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from threecrate_b200 import sharding, synth
+from threecrate_b200 import sharding
+from fixtures import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

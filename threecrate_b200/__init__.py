@@ -3,7 +3,7 @@ rajgandhi1/threecrate, behind the reference's operator interface.
 
   csrc/      hand-written CUDA kernels + the C ABI (include/threecrate_cuda.h)
   api.py     host-side mirror of the reference functions (ctypes over the C ABI)
-  synth.py   deterministic synthetic clouds for the BASELINE.json configs
+  (synthetic clouds / reference fixtures live outside the package: fixtures/synth.py)
   build.py   in-tree nvcc build of lib/libthreecrate_cuda.so
 
 The CUDA library is the only compute path: importing `api` symbols works on a CPU box (for
@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     GridIndex,
     ICPResult,
     IDENTITY,
+    DEFAULT_SEARCH_FLAGS,
     IcpScaleLevel,
     MultiScaleIcpConfig,
     InvalidData,

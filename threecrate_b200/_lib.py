@@ -45,6 +45,18 @@ class IndexInfoC(C.Structure):
                 ("n_levels", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+TC_STATS_MAX_ITERS = 64
+
+
+class StatsC(C.Structure):
+    _fields_ = [("queries", C.c_uint64), ("chain_queries", C.c_uint64), ("rounds", C.c_uint64),
+                ("box_splits", C.c_uint64), ("retries", C.c_uint64),
+                ("candidates_staged", C.c_uint64), ("merges", C.c_uint64),
+                ("icp_iterations", C.c_uint32), ("reserved", C.c_uint32),
+                ("icp_mse", C.c_float * TC_STATS_MAX_ITERS),
+                ("icp_valid", C.c_uint64 * TC_STATS_MAX_ITERS)]
+
+
 _vp = C.c_void_p
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
@@ -66,6 +78,8 @@ SYMBOLS = {
     "tc_timer_start": (C.c_int, [_vp]),
     "tc_timer_stop": (C.c_int, [_vp, _f32p]),
     "tc_version": (C.c_char_p, []),
+    "tc_stats_enable": (C.c_int, [_vp, C.c_int]),
+    "tc_last_stats": (C.c_int, [_vp, C.POINTER(StatsC)]),
     "tc_cloud_upload": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "tc_cloud_upload_strided": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
     "tc_cloud_from_device": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),

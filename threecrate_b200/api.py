@@ -88,6 +88,23 @@ class Context:
         self.check(self.lib.tc_timer_stop(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def enable_stats(self, on: bool = True):
+        """Collect per-call statistics (tc_stats_enable); off by default."""
+        self.check(self.lib.tc_stats_enable(self.h, 1 if on else 0))
+
+    def last_stats(self) -> dict:
+        """tc_last_stats: counters of the last kNN / normals launch and the per-iteration history
+        of the last ICP call."""
+        s = _lib.StatsC()
+        self.check(self.lib.tc_last_stats(self.h, C.byref(s)))
+        n = int(s.icp_iterations)
+        return {"queries": int(s.queries), "chain_queries": int(s.chain_queries),
+                "rounds": int(s.rounds), "box_splits": int(s.box_splits),
+                "retries": int(s.retries), "candidates_staged": int(s.candidates_staged),
+                "merges": int(s.merges), "icp_iterations": n,
+                "icp_mse": [float(s.icp_mse[i]) for i in range(min(n, _lib.TC_STATS_MAX_ITERS))],
+                "icp_valid": [int(s.icp_valid[i]) for i in range(min(n, _lib.TC_STATS_MAX_ITERS))]}
+
     # raw device memory
     def alloc(self, nbytes: int) -> int:
         p = _vp()
@@ -343,6 +360,9 @@ def estimate_normals_radius(points, radius: float, consistent_orientation: bool,
 # ICP
 # --------------------------------------------------------------------------------------------
 IDENTITY = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+# default search-variant bits of the library (tc_search.cu g_tc_search_flags): per-lane two-pass
+# kernels + Newton eigen solver; |32 selects the staged-tile kernels, |64 their TMA staging
+DEFAULT_SEARCH_FLAGS = 159
 
 
 @dataclass

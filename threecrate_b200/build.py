@@ -18,8 +18,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libthreecrate_cuda.so")
-SOURCES = ["tc_api.cu", "tc_index.cu", "tc_search.cu", "tc_icp.cu", "tc_comm.cu", "tc_filter.cu"]
-HEADERS = ["tc_internal.cuh", "tc_search.cuh", os.path.join(ROOT, "include", "threecrate_cuda.h")]
+SOURCES = ["tc_api.cu", "tc_index.cu", "tc_search.cu", "tc_tile.cu", "tc_icp.cu", "tc_comm.cu",
+           "tc_filter.cu"]
+HEADERS = ["tc_internal.cuh", "tc_search.cuh", "tc_normal.cuh", os.path.join(ROOT, "include", "threecrate_cuda.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -78,6 +78,31 @@ extern "C" const char* tc_last_error(const tc_context* ctx) { return ctx ? ctx->
 extern "C" void* tc_context_stream(tc_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t tc_launch_count(const tc_context* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int tc_stats_enable(tc_context* ctx, int on) {
+  if (!ctx) return TC_INVALID_DATA;
+  ctx->stats_on = on != 0;
+  return TC_OK;
+}
+extern "C" int tc_last_stats(tc_context* ctx, tc_stats* out) {
+  TC_ENTER(ctx);
+  if (!out) return TC_INVALID_DATA;
+  *out = ctx->icp_stats;  // ICP history (zero when no ICP call ran with statistics on)
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ctx->stats_on) {
+    TC_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch + 48, sizeof(h), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  out->queries = ctx->stats_queries;
+  out->chain_queries = h[0];
+  out->rounds = h[1];
+  out->box_splits = h[2];
+  out->retries = h[3];
+  out->candidates_staged = h[4];
+  out->merges = h[5];
+  return TC_OK;
+}
+
 extern "C" int tc_context_synchronize(tc_context* ctx) {
   TC_ENTER(ctx);
   TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -679,7 +679,8 @@ __device__ __noinline__ void icp_solve_point(IcpState* st, const double* sums, f
 // transform (registration.rs:342-361).  prev[] holds the last matches (level << 30 | position).
 __global__ void __launch_bounds__(kIcpBlock)
 k_icp_p2p_final_mse(LevelSet ls, const float4* __restrict__ src, uint32_t ns,
-                    const uint32_t* __restrict__ prev, const IcpState* __restrict__ st,
+                    const uint32_t* __restrict__ prev, const uint32_t* __restrict__ match,
+                    const IcpState* __restrict__ st,
                     double* __restrict__ out2 /* [sum, count], zeroed */) {
   float T[7];
 #pragma unroll
@@ -689,6 +690,10 @@ k_icp_p2p_final_mse(LevelSet ls, const float4* __restrict__ src, uint32_t ns,
     const uint32_t m = prev[i];
     if (m == 0xFFFFFFFFu) continue;
     const float4 s4 = __ldg(&src[i]);
+    // prev[] keeps the nearest point as next iteration's seed even when the pair was rejected by
+    // max_correspondence_distance; the reference averages over the ACCEPTED pairs only
+    // (final_correspondences, registration.rs:342-361): `match` (by original source index) has them
+    if (match && match[__float_as_uint(s4.w)] == TC_NO_INDEX) continue;
     V3 s = quat_rotate(T + 3, V3{s4.x, s4.y, s4.z});
     s = V3{xadd(s.x, T[0]), xadd(s.y, T[1]), xadd(s.z, T[2])};
     const float4 t4 = __ldg(&ls.pts[m >> 30][m & 0x3FFFFFFFu]);
@@ -758,6 +763,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
 
   float4* d_nrm = nullptr;
   uint32_t* d_prev = nullptr;
+  uint32_t* d_match_own = nullptr;  // kPoint + max distance: acceptance record for the final mse
   IcpState* d_state = nullptr;
   double *d_partials = nullptr, *d_sums = nullptr, *d_final = nullptr;
   int st = TC_OK;
@@ -766,6 +772,10 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   if (st == TC_OK && nt < (1u << 30) && ns > 0) {
     st = tc_alloc(ctx, &d_prev, ns);
     if (st == TC_OK) cudaMemsetAsync(d_prev, 0xFF, (size_t)ns * sizeof(uint32_t), ctx->stream);
+  }
+  if (st == TC_OK && mode == kPoint && max_corr_dist >= 0.0f && !d_match_out && ns > 0) {
+    st = tc_alloc(ctx, &d_match_own, ns);
+    d_match_out = d_match_own;
   }
   if (st == TC_OK) st = tc_alloc(ctx, &d_partials, (uint64_t)grid * n_sums);
   if (st == TC_OK) st = tc_alloc(ctx, &d_sums, n_sums);
@@ -818,8 +828,8 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
       // mse of the last correspondences under the final transform (only used when not converged)
       cudaMemsetAsync(d_final, 0, 2 * sizeof(double), ctx->stream);
       if (ns > 0) {
-        k_icp_p2p_final_mse<<<grid, kIcpBlock, 0, ctx->stream>>>(ls, d_src, ns, d_prev, d_state,
-                                                                 d_final);
+        k_icp_p2p_final_mse<<<grid, kIcpBlock, 0, ctx->stream>>>(
+            ls, d_src, ns, d_prev, max_corr_dist >= 0.0f ? d_match_out : nullptr, d_state, d_final);
         ctx->launches++;
       }
       if (comm) st = tci_comm_allreduce(comm, d_final, 2);
@@ -839,6 +849,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   }
   tc_free(ctx, d_src);
   tc_free(ctx, d_prev);
+  tc_free(ctx, d_match_own);
   tc_free(ctx, d_nrm);
   tc_free(ctx, d_state);
   tc_free(ctx, d_partials);

@@ -24,6 +24,9 @@ struct tc_context {
   uint32_t* h_scratch = nullptr;   // pinned + device-visible (UVA), 64 words: kernels publish small
                                    // results here and the host polls a sequence word
   uint32_t seq = 0;                // last sequence number handed to a publishing kernel
+  bool stats_on = false;           // device counters of the search kernels (d_scratch[48..55])
+  uint64_t stats_queries = 0;      // queries of the last search launch
+  tc_stats icp_stats{};            // per-iteration history of the last ICP call (host copy)
   // small grow-only device workspaces reused across calls (index-build histograms, fallback
   // lists): every allocation call costs the host 1-2 us and the LiDAR-frame path is host-bound
   static constexpr int kWsSlots = 3;
@@ -142,6 +145,7 @@ inline int tc_ws_get(tc_context* ctx, int slot, T** p, uint64_t count) {
     if (ctx->ws[slot]) cudaFreeAsync(ctx->ws[slot], ctx->stream);
     ctx->ws[slot] = nullptr;
     ctx->ws_bytes[slot] = 0;
+    ctx->ws_zero[slot] = false;  // the pool may hand back the same base address: contents unknown
     const uint64_t grown = bytes + bytes / 4;
     TC_CUDA(ctx, cudaMallocAsync(&ctx->ws[slot], grown, ctx->stream));
     ctx->ws_bytes[slot] = grown;
@@ -158,10 +162,9 @@ inline void tc_ws_release(tc_context* ctx, int slot, void* p) {
 // restored = false and the next user clears the buffer.
 template <typename T>
 inline int tc_ws_get_zeroed(tc_context* ctx, int slot, T** p, uint64_t count) {
-  const void* before = ctx->ws[slot];
-  TC_TRY(tc_ws_get(ctx, slot, p, count));
+  TC_TRY(tc_ws_get(ctx, slot, p, count));  // (a reallocation clears ws_zero)
   const bool cached = ((void*)*p == ctx->ws[slot]);
-  if (!cached || before != ctx->ws[slot] || !ctx->ws_zero[slot]) {
+  if (!cached || !ctx->ws_zero[slot]) {
     const uint64_t bytes = cached ? ctx->ws_bytes[slot] : std::max<uint64_t>(count, 1) * sizeof(T);
     TC_CUDA(ctx, cudaMemsetAsync(*p, 0, bytes, ctx->stream));
   }
@@ -201,6 +204,16 @@ int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radi
                               int orient, const float vp[3], float* d_out_aos);
 int tci_radius_search_launch(tc_context* ctx, const tc_index* index, const float q[3], float radius,
                              uint32_t* d_idx, float* d_d2, uint32_t capacity, uint32_t* d_count);
+
+// tc_tile.cu — staged-tile kernels (shape: 16, 17, 32, 33 list slots; flags: search variant bits)
+int tci_tile_normals(tc_context* ctx, const LevelSet& ls, int shape, uint32_t q_begin,
+                     uint32_t q_end, uint32_t own_begin, uint32_t own_end, uint32_t k, int orient,
+                     const float vp[3], float* d_out, uint32_t* d_fb_list, uint32_t* d_fb_count,
+                     uint32_t* d_stats, int flags);
+int tci_tile_knn(tc_context* ctx, const LevelSet& ls, int shape, const float4* d_queries,
+                 uint32_t q_begin, uint32_t q_end, uint32_t k, uint32_t need, int drop_self,
+                 uint32_t* d_idx, float* d_dist, uint32_t* d_count, uint32_t* d_fb_list,
+                 uint32_t* d_fb_count, uint32_t* d_stats, int flags);
 
 // tc_icp.cu — GICP building blocks (gicp.rs): per-point covariances as two float4
 // {xx, xy, xz, yy | yz, zz, 0, 0} by original index, and the Gauss-Newton loop

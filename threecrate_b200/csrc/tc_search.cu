@@ -12,6 +12,7 @@
 // The search is exact: ring r of cells is added until the K-th best d2 is below the (conservative)
 // squared distance from the query to the boundary of the searched block of cells.
 #include "tc_search.cuh"
+#include "tc_normal.cuh"
 
 namespace {
 
@@ -224,106 +225,13 @@ k_knn2(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32
            count_out);
 }
 
-// ------------------------------------------------------------------------- symmetric 3x3 eigen
-// Cyclic Jacobi in f64 on the f32 covariance the reference would hand to nalgebra's
-// symmetric_eigen (normals.rs:181).  Returns the unit eigenvector of the smallest eigenvalue
-// (first strict minimum, normals.rs:186-191).
-__device__ __forceinline__ void smallest_eigvec(const float cov[6] /*xx,xy,xz,yy,yz,zz*/,
-                                                float n[3]) {
-  double a00 = cov[0], a01 = cov[1], a02 = cov[2], a11 = cov[3], a12 = cov[4], a22 = cov[5];
-  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // v[row][col]
-#define TC_JACOBI(app, aqq, apq, arp, arq, P, Q)                                   \
-  if (apq != 0.0) {                                                                \
-    const double theta = (aqq - app) / (2.0 * apq);                                \
-    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
-    const double c = rsqrt(t * t + 1.0), s = t * c;                                \
-    app = app - t * apq;                                                           \
-    aqq = aqq + t * apq;                                                           \
-    apq = 0.0;                                                                     \
-    const double rp = arp, rq = arq;                                               \
-    arp = c * rp - s * rq;                                                         \
-    arq = s * rp + c * rq;                                                         \
-    _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                \
-      const double vp = v[r][P], vq = v[r][Q];                                     \
-      v[r][P] = c * vp - s * vq;                                                   \
-      v[r][Q] = s * vp + c * vq;                                                   \
-    }                                                                              \
-  }
-  for (int sweep = 0; sweep < 10; ++sweep) {
-    const double off = a01 * a01 + a02 * a02 + a12 * a12;
-    const double dg = a00 * a00 + a11 * a11 + a22 * a22;
-    if (off <= 1e-30 * dg || off == 0.0) break;
-    TC_JACOBI(a00, a11, a01, a02, a12, 0, 1)  // (p,q) = (0,1); third index r = 2
-    TC_JACOBI(a00, a22, a02, a01, a12, 0, 2)  // (0,2); r = 1  (a01 = a_{r p}, a12 = a_{r q})
-    TC_JACOBI(a11, a22, a12, a01, a02, 1, 2)  // (1,2); r = 0
-  }
-#undef TC_JACOBI
-  int m = 0;
-  double lm = a00;
-  if (a11 < lm) {
-    lm = a11;
-    m = 1;
-  }
-  if (a22 < lm) {
-    lm = a22;
-    m = 2;
-  }
-  const double ex = m == 0 ? v[0][0] : (m == 1 ? v[0][1] : v[0][2]);
-  const double ey = m == 0 ? v[1][0] : (m == 1 ? v[1][1] : v[1][2]);
-  const double ez = m == 0 ? v[2][0] : (m == 1 ? v[2][1] : v[2][2]);
-  n[0] = (float)ex;
-  n[1] = (float)ey;
-  n[2] = (float)ez;
-}
-
-// covariance (f32, already divided by n) -> unit eigenvector of the smallest eigenvalue,
-// renormalised, +z for a vanishing vector (normals.rs:181-202)
-__device__ __forceinline__ void normal_from_cov(const float c[6], float nrm[3]) {
-  smallest_eigvec(c, nrm);
-  const float mag =
-      xsqrt(xadd(xadd(xmul(nrm[0], nrm[0]), xmul(nrm[1], nrm[1])), xmul(nrm[2], nrm[2])));
-  if (mag > 1e-6f) {
-    nrm[0] = xdiv(nrm[0], mag);
-    nrm[1] = xdiv(nrm[1], mag);
-    nrm[2] = xdiv(nrm[2], mag);
-  } else {
-    nrm[0] = 0.0f;
-    nrm[1] = 0.0f;
-    nrm[2] = 1.0f;
-  }
-}
-// orientation (normals.rs:208-222: flip iff n . normalize(vp - p) < 0) and the NormalPoint3f row
-__device__ __forceinline__ void write_normal(float nrm[3], const float4 q, uint32_t qid, int orient,
-                                             float vpx, float vpy, float vpz,
-                                             float* __restrict__ out) {
-  if (orient) {
-    float tx = xsub(vpx, q.x), ty = xsub(vpy, q.y), tz = xsub(vpz, q.z);
-    const float mag = xsqrt(xadd(xadd(xmul(tx, tx), xmul(ty, ty)), xmul(tz, tz)));
-    tx = xdiv(tx, mag);
-    ty = xdiv(ty, mag);
-    tz = xdiv(tz, mag);
-    const float d = xadd(xadd(xmul(nrm[0], tx), xmul(nrm[1], ty)), xmul(nrm[2], tz));
-    if (d < 0.0f) {
-      nrm[0] = -nrm[0];
-      nrm[1] = -nrm[1];
-      nrm[2] = -nrm[2];
-    }
-  }
-  float* o = out + 6 * (uint64_t)qid;
-  o[0] = q.x;
-  o[1] = q.y;
-  o[2] = q.z;
-  o[3] = nrm[0];
-  o[4] = nrm[1];
-  o[5] = nrm[2];
-}
-
 // ------------------------------------------------------------------------------ normals kernel
 // Normal of one point from its ascending (d2, index) neighbour keys (normals.rs:306-354 body).
 template <class KS>
 __device__ __forceinline__ void normals_emit(const KS& keys, const float4 q, uint32_t qid,
                                              uint32_t k, int orient, float vpx, float vpy,
-                                             float vpz, float* __restrict__ out) {
+                                             float vpz, float* __restrict__ out,
+                                             bool fast = false) {
   // neighbourhood = first k of kNN(k+1) with self dropped by index, then self appended last
   // (normals.rs:148-153, 338-340).  Sums are sequential f32 in that order (normals.rs:165-177).
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
@@ -382,7 +290,7 @@ __device__ __forceinline__ void normals_emit(const KS& keys, const float4 q, uin
     acc(q.x, q.y, q.z);
 #pragma unroll
     for (int i = 0; i < 6; ++i) c[i] = xdiv(c[i], fn);
-    normal_from_cov(c, nrm);
+    normal_from_cov(c, nrm, fast);
   }
   write_normal(nrm, q, qid, orient, vpx, vpy, vpz, out);
 }
@@ -440,7 +348,7 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
     return;
   }
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
-               out);
+               out, (ls.g[0].flags & 128) != 0);
   if (dbg) {
     dbg[0] = (uint32_t)(clock64() - t0);
     dbg[1] = (uint32_t)n | ((uint32_t)level << 16);
@@ -664,7 +572,9 @@ inline int pick_size(uint32_t need) {
 
 }  // namespace
 
-int g_tc_search_flags = 31;
+// bit 5 (32): staged-tile kernels (tc_tile.cu); bit 6 (64): TMA bulk staging (else LDG/STS);
+// bit 7 (128): Newton eigen solver with Jacobi fallback
+int g_tc_search_flags = 159;  // per-lane kernels + Newton; the staged-tile variant measured 13-17 % slower
 static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (8 u32 / point)
 extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
 extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint32_t*)d_buf; }
@@ -743,14 +653,26 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   k_knn2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,   \
                                                    (uint32_t)q_end, k, need, drop_self,       \
                                                    d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)
-  switch (two_pass_shape(need, flags)) {
-    case 16: TC_KNN2(16, false); break;
-    case 17: TC_KNN2(16, true); break;
-    case 32: TC_KNN2(32, false); break;
-    default: TC_KNN2(32, true); break;
+  if (flags & 32) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+    uint32_t* d_stats = nullptr;
+    ctx->stats_queries = nq;
+    if (ctx->stats_on) {
+      d_stats = ctx->d_scratch + 48;
+      TC_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(uint32_t), ctx->stream));
+    }
+    TC_TRY(tci_tile_knn(ctx, ls, two_pass_shape(need, flags), d_queries_sorted, (uint32_t)q_begin,
+                        (uint32_t)q_end, k, need, drop_self, d_idx_out, d_dist_out, d_count_out,
+                        d_fb + 1, d_fb, d_stats, flags));
+  } else {
+    switch (two_pass_shape(need, flags)) {
+      case 16: TC_KNN2(16, false); break;
+      case 17: TC_KNN2(16, true); break;
+      case 32: TC_KNN2(32, false); break;
+      default: TC_KNN2(32, true); break;
+    }
+    TC_LAUNCHED(ctx);
   }
 #undef TC_KNN2
-  TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_knn<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
                         ls, d_queries_sorted, 0u, 0u, k, need, drop_self, d_idx_out, d_dist_out,
@@ -810,14 +732,26 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
       ls, (uint32_t)q_begin, (uint32_t)q_end, own_begin, own_end, k, orient, vp[0], vp[1],   \
       vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg)
-  switch (two_pass_shape(k + 1, flags)) {
-    case 16: TC_NORMALS2(16, false); break;
-    case 17: TC_NORMALS2(16, true); break;
-    case 32: TC_NORMALS2(32, false); break;
-    default: TC_NORMALS2(32, true); break;
+  if (flags & 32) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+    uint32_t* d_stats = nullptr;
+    ctx->stats_queries = nq;
+    if (ctx->stats_on) {
+      d_stats = ctx->d_scratch + 48;
+      TC_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(uint32_t), ctx->stream));
+    }
+    TC_TRY(tci_tile_normals(ctx, ls, two_pass_shape(k + 1, flags), (uint32_t)q_begin,
+                            (uint32_t)q_end, own_begin, own_end, k, orient, vp, d_out_aos, d_fb + 1,
+                            d_fb, d_stats, flags));
+  } else {
+    switch (two_pass_shape(k + 1, flags)) {
+      case 16: TC_NORMALS2(16, false); break;
+      case 17: TC_NORMALS2(16, true); break;
+      case 32: TC_NORMALS2(32, false); break;
+      default: TC_NORMALS2(32, true); break;
+    }
+    TC_LAUNCHED(ctx);
   }
 #undef TC_NORMALS2
-  TC_LAUNCHED(ctx);
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
                         ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],

@@ -10,12 +10,14 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import threecrate_b200 as tc  # noqa: E402
-from threecrate_b200 import _lib, synth  # noqa: E402
+from threecrate_b200 import _lib  # noqa: E402
+from fixtures import synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--flags", default="0,1,2,3")
 ap.add_argument("--what", default="c2,c4,c3")
 ap.add_argument("--c4n", type=int, default=2_000_000)
+ap.add_argument("--c4k", default="30")
 ap.add_argument("--cellscale", default="1.0")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--finecap", type=int, default=0)
@@ -67,9 +69,19 @@ def normals_case(name, pts, k):
             if ref is None:
                 ref = out
             same = np.array_equal(ref, out)
+            a_, b_ = ref[:, 3:].astype(np.float64), out[:, 3:].astype(np.float64)
+            ang = np.arctan2(np.linalg.norm(np.cross(a_, b_), axis=1), (a_ * b_).sum(1))
+            ctx.enable_stats(True)
+            index.estimate_normals_device(d_out, k)
+            st = ctx.last_stats()
+            ctx.enable_stats(False)
             print(f"{name:4s} k={k:2d} cell={info['cell_size']:.4f} (x{sc}) occ={info['occupied_cells']} "
                   f"maxpop={info['max_cell_population']} flags={f} kernel={ms:8.3f} ms "
-                  f"{n / ms / 1e3:8.1f} Mpts/s same={same}", flush=True)
+                  f"{n / ms / 1e3:8.1f} Mpts/s same={same} pos_same={np.array_equal(ref[:, :3], out[:, :3])} "
+                  f"ang max={ang.max():.2e} n>1e-5={(ang > 1e-5).sum()} "
+                  f"chain={st['chain_queries']} rounds={st['rounds']} splits={st['box_splits']} "
+                  f"retries={st['retries']} cand/round={st['candidates_staged'] / max(st['rounds'], 1):.0f} "
+                  f"merges/round={st['merges'] / max(st['rounds'], 1):.1f}", flush=True)
         if index is not base_index:
             index.free()
     ctx.free(d_out)
@@ -80,7 +92,9 @@ if "c2" in what:
     normals_case("c2", synth.kitti_frame(), 16)
 if "c4" in what:
     n = a.c4n
-    normals_case("c4", synth.terrain(n, 100.0 * (n / 1e7) ** 0.5, seed=4, noise=0.002), 30)
+    c4pts = synth.terrain(n, 100.0 * (n / 1e7) ** 0.5, seed=4, noise=0.002)
+    for kk in a.c4k.split(","):
+        normals_case("c4", c4pts, int(kk))
 if "c3" in what:
     n = 1_000_000
     src, tgt, nrm, T = synth.scan_pair(n, half_extent=50.0)

@@ -11,7 +11,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import threecrate_b200 as tc  # noqa: E402
-from threecrate_b200 import synth  # noqa: E402
+from fixtures import synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["c2", "c4", "c3", "knn", "gicp", "filters"])

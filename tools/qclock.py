@@ -5,7 +5,8 @@ import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import threecrate_b200 as tc
-from threecrate_b200 import _lib, synth
+from threecrate_b200 import _lib
+from fixtures import synth
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 15
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 16
