@@ -130,6 +130,18 @@ int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* cloud, uint3
 int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
                    tc_index** out);
 void tc_index_free(tc_index* index);
+/* Multi-GPU normals (queries sharded, one process per GPU, no data-path collective): every rank
+ * calls this on ITS copy of the same cloud.  The ranks agree on one grid (bbox, cell size and
+ * level decisions come from the whole cloud), cut it into `world` slabs of whole cell planes along
+ * its longest axis, and rank `rank` sorts only the points of its slab plus a halo of a few planes -
+ * the counting-sort scatter, the cell-range scan and the shared-memory-sized tables shrink by
+ * ~1/world.  tc_estimate_normals_device on such an index computes exactly the rank's own rows
+ * (pass shard range [0, UINT64_MAX)); should a query ever need points beyond the halo the call
+ * transparently finishes on a complete index, so results never depend on the sharding.  Clouds that
+ * need several grid resolutions, or have fewer planes than ranks, get a complete index and the
+ * rank's share of its sorted order instead.  kNN / ICP entry points need a complete index. */
+int tc_index_build_sharded(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
+                           int rank, int world, tc_index** out);
 
 typedef struct tc_index_info {
   uint64_t n_points;

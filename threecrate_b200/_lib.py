@@ -91,6 +91,8 @@ SYMBOLS = {
     "tc_statistical_outlier_removal": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, C.c_int, _vp,
                                                  C.POINTER(_vp)]),
     "tc_index_build": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, C.POINTER(_vp)]),
+    "tc_index_build_sharded": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, C.c_int, C.c_int,
+                                         C.POINTER(_vp)]),
     "tc_index_free": (None, [_vp]),
     "tc_index_get_info": (C.c_int, [_vp, C.POINTER(IndexInfoC)]),
     "tc_knn": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp, _vp, _vp]),

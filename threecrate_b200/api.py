@@ -105,6 +105,14 @@ class Context:
                 "icp_mse": [float(s.icp_mse[i]) for i in range(min(n, _lib.TC_STATS_MAX_ITERS))],
                 "icp_valid": [int(s.icp_valid[i]) for i in range(min(n, _lib.TC_STATS_MAX_ITERS))]}
 
+    def issue_rate(self) -> float:
+        """Measured warp-instruction issue ceiling of the device (debug microbenchmark)."""
+        self.lib.tc_debug_issue_rate.argtypes = [_vp, C.POINTER(C.c_double)]
+        self.lib.tc_debug_issue_rate.restype = C.c_int
+        v = C.c_double()
+        self.check(self.lib.tc_debug_issue_rate(self.h, C.byref(v)))
+        return float(v.value)
+
     # raw device memory
     def alloc(self, nbytes: int) -> int:
         p = _vp()
@@ -162,6 +170,17 @@ class DeviceCloud:
         self.h = h
 
     @classmethod
+    def from_device(cls, d_xyz: int, n: int, ctx: Optional["Context"] = None) -> "DeviceCloud":
+        """Wrap (copy) n x 3 f32 AoS points that already live in device memory
+        (tc_cloud_from_device) - e.g. a torch / cupy buffer's data pointer."""
+        ctx = ctx or default_context()
+        h = _vp()
+        ctx.check(ctx.lib.tc_cloud_from_device(ctx.h, _vp(int(d_xyz)), int(n), C.byref(h)))
+        c = cls.__new__(cls)
+        c.ctx, c.h, c.n = ctx, h, int(n)
+        return c
+
+    @classmethod
     def _from_handle(cls, ctx: "Context", h) -> "DeviceCloud":
         c = cls.__new__(cls)
         c.ctx, c.h = ctx, h
@@ -192,12 +211,21 @@ class DeviceCloud:
 class GridIndex:
     """Uniform-grid spatial index over a DeviceCloud (tc_index) — the KdTree::new replacement."""
 
-    def __init__(self, cloud: DeviceCloud, k_hint: int = 16, cell_size: float = 0.0):
+    def __init__(self, cloud: DeviceCloud, k_hint: int = 16, cell_size: float = 0.0,
+                 shard: Optional[tuple] = None):
+        """shard=(rank, world): slab-sharded build for multi-GPU normals
+        (tc_index_build_sharded) - estimate_normals_device then writes this rank's rows only."""
         self.cloud = cloud
         self.ctx = cloud.ctx
+        self.shard = shard
         h = _vp()
-        self.ctx.check(self.ctx.lib.tc_index_build(self.ctx.h, cloud.h, int(k_hint),
-                                                   float(cell_size), C.byref(h)))
+        if shard is None:
+            self.ctx.check(self.ctx.lib.tc_index_build(self.ctx.h, cloud.h, int(k_hint),
+                                                       float(cell_size), C.byref(h)))
+        else:
+            self.ctx.check(self.ctx.lib.tc_index_build_sharded(
+                self.ctx.h, cloud.h, int(k_hint), float(cell_size), int(shard[0]), int(shard[1]),
+                C.byref(h)))
         self.h = h
 
     def info(self) -> dict:
@@ -255,6 +283,8 @@ class GridIndex:
         ctx = self.ctx
         vp = None if viewpoint is None else np.ascontiguousarray(viewpoint, np.float32)
         end = self.cloud.n if shard[1] is None else int(shard[1])
+        if self.shard is not None and shard == (0, None):
+            end = 0xFFFFFFFFFFFFFFFF  # the rank's own rows of a tc_index_build_sharded index
         ctx.check(ctx.lib.tc_estimate_normals_device(
             ctx.h, self.h, int(k), -1.0, int(bool(consistent_orientation)),
             None if vp is None else _vp(vp.ctypes.data), int(shard[0]), end, _vp(d_out)))

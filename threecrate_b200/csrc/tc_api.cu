@@ -66,6 +66,8 @@ extern "C" void tc_context_destroy(tc_context* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < tc_context::kWsSlots; ++i)
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+  for (int i = 0; i < tc_context::kArenaSlots; ++i)
+    if (ctx->arena_cache[i]) cudaFree(ctx->arena_cache[i]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -100,6 +102,55 @@ extern "C" int tc_last_stats(tc_context* ctx, tc_stats* out) {
   out->retries = h[3];
   out->candidates_staged = h[4];
   out->merges = h[5];
+  return TC_OK;
+}
+
+// Measured instruction-issue ceiling (the second roofline bench.py reports: exact kNN is bounded
+// by issue slots, not by HBM).  Every thread runs 16 independent dependency chains, half FMNMX
+// (ALU pipe) and half FMUL (FMA pipe) - the mix of the selection networks and the distance code -
+// so the schedulers always have an eligible instruction: warp-instructions per second.
+namespace {
+__global__ void __launch_bounds__(256) k_issue_rate(float* out, int iters, float seed) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+  const float lim = seed * 1e30f, c = 1.0f + seed * 1e-7f;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        a[i] = fminf(a[i], lim);      // FMNMX (ALU pipe); the FMUL in between keeps ptxas from
+        a[i] = __fmul_rn(a[i], c);    // pairing two of them into one FMNMX3
+      }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;  // keeps the loop alive
+}
+}  // namespace
+extern "C" int tc_debug_issue_rate(tc_context* ctx, double* warp_inst_per_s) {
+  TC_ENTER(ctx);
+  if (!warp_inst_per_s) return TC_INVALID_DATA;
+  float* d = nullptr;
+  TC_TRY(tc_alloc(ctx, &d, 1));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    TC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    k_issue_rate<<<blocks, 256, 0, ctx->stream>>>(d, iters, 0.5f);
+    TC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    TC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f;
+    TC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  tc_free(ctx, d);
+  const double inst = (double)blocks * 8.0 /*warps*/ * (double)iters * 128.0 /*math per trip*/;
+  *warp_inst_per_s = inst / ((double)best * 1e-3);
   return TC_OK;
 }
 
@@ -284,6 +335,8 @@ extern "C" int tc_knn_device(tc_context* ctx, const tc_index* ix, const float* d
                              float* d_dist_out, uint32_t* d_count_out) {
   TC_ENTER(ctx);
   if (!ix) return TC_INVALID_DATA;
+  if (ix->sharded)
+    return tc_fail(ctx, TC_INVALID_DATA, "a slab-sharded index serves tc_estimate_normals_device only");
   const bool self_query = (d_queries_aos == nullptr);
   if (self_query && nq != ix->n)
     return tc_fail(ctx, TC_INVALID_DATA, "self query: nq must equal the indexed cloud's length");
@@ -357,6 +410,8 @@ extern "C" int tc_radius_search(tc_context* ctx, const tc_index* ix, const float
                                 uint64_t* n_found) {
   TC_ENTER(ctx);
   if (!ix || !query || !n_found) return TC_INVALID_DATA;
+  if (ix->sharded)
+    return tc_fail(ctx, TC_INVALID_DATA, "a slab-sharded index serves tc_estimate_normals_device only");
   *n_found = 0;
   if (!(radius > 0.0f) || ix->n == 0) return TC_OK;  // nearest_neighbor.rs:255-257
   for (int a = 0; a < 3; ++a)
@@ -431,6 +486,10 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
   if (ix->n == 0) return TC_OK;  // empty -> Ok(empty), checked before k (normals.rs:261-263)
   if (k < 3) return tc_fail(ctx, TC_INVALID_DATA, "k_neighbors must be at least 3");
   if (!d_out_aos) return TC_INVALID_DATA;
+  if (shard_end == UINT64_MAX && shard_begin == 0 && ix->shard_world > 1 && !ix->sharded) {
+    shard_begin = ix->own_lo;  // complete index from tc_index_build_sharded: the rank's share
+    shard_end = ix->own_hi;
+  }
   if (shard_end > ix->n) shard_end = ix->n;
   float vp[3];
   if (viewpoint3) {
@@ -441,12 +500,44 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
     default_viewpoint(ix->bbox_min, ix->bbox_max, vp);
   }
   if (radius > 0.0f) {  // Some(radius); radius <= 0 finds nothing and is the kNN rule for everyone
-    if (shard_begin != 0 || shard_end < ix->n)
+    if (shard_begin != 0 || shard_end < ix->n || ix->sharded)
       return tc_fail(ctx, TC_INVALID_DATA, "radius-mode normals are not sharded; pass the full range");
     return tci_normals_radius_launch(ctx, ix, radius, k, consistent_orientation ? 1 : 0, vp, d_out_aos);
   }
-  return tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, shard_begin, shard_end,
-                            d_out_aos);
+  if (!ix->sharded)
+    return tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, shard_begin, shard_end,
+                              d_out_aos);
+  // Slab-sharded index: exactly the rank's own rows.  A search that had to look beyond the halo
+  // (counted on the device) may have missed points of the unbuilt part: the rows are then redone
+  // on a complete index, whose sorted range of the same planes holds the same queries.
+  uint32_t* d_unsafe = ctx->d_scratch + 42;
+  TC_CUDA(ctx, cudaMemsetAsync(d_unsafe, 0, sizeof(uint32_t), ctx->stream));
+  TC_TRY(tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, ix->own_lo, ix->own_hi,
+                            d_out_aos, true));
+  uint32_t* h = ctx->h_scratch + 47;
+  TC_CUDA(ctx, cudaMemcpyAsync(h, d_unsafe, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*h == 0) return TC_OK;
+  tc_index* full = nullptr;
+  TC_TRY(tci_index_build(ctx, ix->cloud, ix->k_hint, ix->cell_size_arg, 0, 1, &full));
+  int st = TC_OK;
+  if (full->n_levels != 1 || full->lv[0].n_cells != ix->lv[0].n_cells) {
+    st = tc_fail(ctx, TC_GPU, "sharded normals: the complete index chose a different grid");
+  } else {
+    uint32_t r[2];
+    cudaError_t e = cudaMemcpyAsync(&r[0], full->lv[0].d_cell_start + ix->own_cell_lo, 4,
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&r[1], full->lv[0].d_cell_start + ix->own_cell_hi, 4,
+                          cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = tc_fail(ctx, TC_GPU, "sharded normals: range readback failed");
+    else
+      st = tci_normals_launch(ctx, full, k, consistent_orientation ? 1 : 0, vp, r[0], r[1], d_out_aos,
+                              true);
+  }
+  tc_index_free(full);
+  return st;
 }
 
 extern "C" int tc_estimate_normals_indexed(tc_context* ctx, const tc_index* ix, uint32_t k,

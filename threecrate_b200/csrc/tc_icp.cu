@@ -725,6 +725,8 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
                     uint32_t* d_match_out) {
   if (!ctx || !src || !tgt || !out || !init) return TC_INVALID_DATA;
   // validation order of registration.rs:266-276 / 517-531 (normals length: host wrapper)
+  if (tgt->sharded)
+    return tc_fail(ctx, TC_INVALID_DATA, "ICP needs a complete target index (not a slab-sharded one)");
   if ((src->n == 0 && !comm) || tgt->n == 0)
     return tc_fail(ctx, TC_INVALID_DATA, "Source or target point cloud is empty");
   if (mode == kPlane && !d_tgt_normals_aos)
@@ -757,6 +759,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
     sg.ny = (int)std::floor((mx[1] - mn[1]) / cell) + 1;
     sg.nz = (int)std::floor((mx[2] - mn[2]) / cell) + 1;
     sg.n = ns;
+    sg.ymajor = tgt->lv[tgt->primary].g.ymajor;  // walk the target's planes in its own order
     TC_TRY(tci_sort_by_grid(ctx, src->d_xyz, ns, sg, &d_src));
   }
   const int grid = std::max(1, std::min((int)((ns + kIcpBlock - 1) / kIcpBlock), ctx->sm_count * 4));

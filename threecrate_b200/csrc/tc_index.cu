@@ -22,18 +22,19 @@ namespace {
 
 // TC_TRACE=1: print host-side phase timings of tc_index_build (adds stream syncs; debug only)
 struct PhaseTrace {
-  bool on;
+  bool on, sync;  // TC_TRACE=1: phases with stream syncs; TC_TRACE=2: host time only, no syncs
   tc_context* ctx;
   std::chrono::steady_clock::time_point t0;
-  explicit PhaseTrace(tc_context* c) : on(std::getenv("TC_TRACE") != nullptr), ctx(c) {
+  explicit PhaseTrace(tc_context* c) : on(std::getenv("TC_TRACE") != nullptr), sync(true), ctx(c) {
     if (on) {
-      cudaStreamSynchronize(ctx->stream);
+      sync = std::atoi(std::getenv("TC_TRACE")) != 2;
+      if (sync) cudaStreamSynchronize(ctx->stream);
       t0 = std::chrono::steady_clock::now();
     }
   }
   void mark(const char* what) {
     if (!on) return;
-    cudaStreamSynchronize(ctx->stream);
+    if (sync) cudaStreamSynchronize(ctx->stream);
     const auto t1 = std::chrono::steady_clock::now();
     fprintf(stderr, "[tc_index_build] %-22s %8.1f us\n", what,
             std::chrono::duration<double, std::micro>(t1 - t0).count());
@@ -145,6 +146,7 @@ struct LevelJob {
   uint32_t* counts;            // n_cells + 1 (histogram, then scatter cursor)
   const uint32_t* cell_start;  // n_cells + 1 (scatter only)
   float4* out;                 // n (scatter only)
+  uint32_t cell_lo, cell_hi;   // only cells in [cell_lo, cell_hi) take part (slab-sharded build)
 };
 struct LevelJobs {
   int n;
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
       // warp-aggregated: consecutive points of a scan usually share a cell, and coarse levels
       // funnel thousands of points into one counter
       const uint32_t peers = __match_any_sync(active, c);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && c >= jobs.l[l].cell_lo &&
+          c < jobs.l[l].cell_hi)
         atomicAdd(&jobs.l[l].counts[c], (uint32_t)__popc(peers));
     }
   }
@@ -259,14 +262,37 @@ __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __rest
       // (warp-aggregated: one atomic per distinct cell per warp)
       const uint32_t peers = __match_any_sync(active, c);
       const int leader = __ffs(peers) - 1;
+      const bool in = c >= jb.cell_lo && c < jb.cell_hi;  // (uniform across the peers)
       uint32_t old = 0;
-      if (lane == leader) old = atomicSub(&jb.counts[c], (uint32_t)__popc(peers));
+      if (lane == leader && in) old = atomicSub(&jb.counts[c], (uint32_t)__popc(peers));
       old = __shfl_sync(active, old, leader);
-      const uint32_t pos =
-          __ldg(&jb.cell_start[c]) + old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      jb.out[pos] = v;
+      if (in) {
+        const uint32_t pos =
+            __ldg(&jb.cell_start[c]) + old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        jb.out[pos] = v;
+      }
     }
   }
+}
+
+// Slab-sharded build: the cell table keeps its full length (kernels index it by global cell id),
+// but only [cell_lo, cell_hi] was scanned.  Cells in front of the slab get 0 and cells behind it
+// the slab's point count, so every range that leaves the slab is empty; the trial histogram's
+// counters outside the slab are cleared so the cached workspace is all zero again.
+__global__ void __launch_bounds__(kThreads) k_fill_outside(uint32_t* __restrict__ cs,
+                                                           uint32_t* __restrict__ counts,
+                                                           uint64_t n_cells, uint64_t cell_lo,
+                                                           uint64_t cell_hi) {
+  const uint32_t n_local = cs[cell_hi];
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < cell_lo; i += stride) {
+    cs[i] = 0u;
+    if (counts) counts[i] = 0u;
+  }
+  for (uint64_t i = cell_hi + 1 + tid; i <= n_cells; i += stride) cs[i] = n_local;
+  if (counts)
+    for (uint64_t i = cell_hi + tid; i <= n_cells; i += stride) counts[i] = 0u;
 }
 
 // ---------------------------------------------------------------------- exclusive scan (u32)
@@ -674,6 +700,7 @@ GridParams make_grid(const float mn[3], const float mx[3], float cell, uint64_t 
     cell *= 1.26f;  // ~2x fewer cells per step
   }
   if (g.nx < 1) g.nx = g.ny = g.nz = 1;
+  g.ymajor = g.ny >= g.nz ? 1 : 0;
   g.cell = cell;
   g.inv = 1.0f / cell;
   return g;
@@ -707,6 +734,8 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   jobs.n = 1;
   jobs.l[0].g = g;
   jobs.l[0].counts = d_counts;
+  jobs.l[0].cell_lo = 0u;
+  jobs.l[0].cell_hi = 0xFFFFFFFFu;
   k_hist_levels<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n,
                                                                          jobs);
   TC_LAUNCHED(ctx);
@@ -728,8 +757,21 @@ extern "C" void tc_debug_set_max_levels(int n) {
   g_tc_max_levels = n < 1 ? 1 : (n > kMaxLevels ? kMaxLevels : n);
 }
 
+int g_tc_shard_halo = 4;  // planes built beyond the rank's own slab on either side
+extern "C" void tc_debug_set_shard_halo(int planes) { g_tc_shard_halo = planes < 1 ? 1 : planes; }
+
 extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint,
                               float cell_size, tc_index** out) {
+  return tci_index_build(ctx, cloud, k_hint, cell_size, 0, 1, out);
+}
+extern "C" int tc_index_build_sharded(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint,
+                                      float cell_size, int rank, int world, tc_index** out) {
+  if (world < 1 || rank < 0 || rank >= world) return tc_fail(ctx, TC_INVALID_DATA, "rank out of range");
+  return tci_index_build(ctx, cloud, k_hint, cell_size, rank, world, out);
+}
+
+int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
+                    int rank, int world, tc_index** out) {
   if (!ctx || !cloud || !out) return TC_INVALID_DATA;
   *out = nullptr;
   const uint64_t n = cloud->n;
@@ -738,6 +780,13 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   ix->ctx = ctx;
   ix->cloud = cloud;
   ix->n = n;
+  ix->n_local = n;
+  ix->k_hint = k_hint;
+  ix->cell_size_arg = cell_size;
+  ix->shard_rank = rank;
+  ix->shard_world = world;
+  ix->own_lo = rank * n / (uint64_t)world;  // complete index: the rank's share of the sorted order
+  ix->own_hi = (rank + 1) * n / (uint64_t)world;
   if (n == 0) {
     ix->n_levels = 1;
     ix->lv[0].g.nx = ix->lv[0].g.ny = ix->lv[0].g.nz = 1;
@@ -856,6 +905,20 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
     pts_off[l] = words;
     words += 4 * n;
   }
+  // Slab-sharded build (one resolution, slabs of whole planes along the slowest axis): this
+  // rank scans / scatters only the cells of its planes +- g_tc_shard_halo.
+  const uint64_t plane = lg[0].ymajor ? (uint64_t)lg[0].nz * lg[0].nx : (uint64_t)lg[0].ny * lg[0].nx;
+  const int n_planes = lg[0].ymajor ? lg[0].ny : lg[0].nz;
+  const bool slab = world > 1 && nl == 1 && n_planes >= 4 * world;
+  uint64_t cell_lo = 0, cell_hi = cells_of(lg[0]), own_cell_lo = 0, own_cell_hi = cell_hi;
+  if (slab) {
+    const int p_lo = (int)((int64_t)rank * n_planes / world),
+              p_hi = (int)((int64_t)(rank + 1) * n_planes / world);
+    own_cell_lo = (uint64_t)p_lo * plane;
+    own_cell_hi = (uint64_t)p_hi * plane;
+    cell_lo = (uint64_t)std::max(p_lo - g_tc_shard_halo, 0) * plane;
+    cell_hi = (uint64_t)std::min(p_hi + g_tc_shard_halo, n_planes) * plane;
+  }
   uint64_t twords = 0, cnt_off[kMaxLevels], tiles = 0;
   for (int l = 0; l < nl; ++l) {
     tiles += (cells_of(lg[l]) + kScanTile - 1) / kScanTile;
@@ -866,8 +929,23 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
   const uint64_t state_off = twords;  // u64 words, 8-byte aligned since twords % 4 == 0
   twords += 2 * (tiles + 1);
   uint32_t* d_tmp = nullptr;
-  st = tc_alloc(ctx, &ix->d_arena, words);
+  trace.mark("host: level decisions");
+  // reuse an arena a freed index left behind (all use is ordered on ctx->stream)
+  for (int a = 0; a < tc_context::kArenaSlots && !ix->d_arena; ++a)
+    if (ctx->arena_cache[a] && ctx->arena_words[a] >= words && ctx->arena_words[a] <= 2 * words + 1024) {
+      ix->d_arena = (uint32_t*)ctx->arena_cache[a];
+      ix->arena_alloc_words = ctx->arena_words[a];
+      ctx->arena_cache[a] = nullptr;
+      ctx->arena_words[a] = 0;
+    }
+  st = TC_OK;
+  if (!ix->d_arena) {
+    st = tc_alloc(ctx, &ix->d_arena, words);
+    ix->arena_alloc_words = words;
+  }
+  trace.mark("host: arena alloc");
   if (st == TC_OK) st = tc_ws_get_zeroed(ctx, 1, &d_tmp, twords);
+  trace.mark("host: workspace");
   bool restored = false;
   LevelJobs all{}, todo{};
   ScanJobs scan{};
@@ -879,10 +957,12 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
       jb.counts = (l == primary && primary_counted) ? d_trial : d_tmp + cnt_off[l];
       jb.cell_start = ix->d_arena + cs_off[l];
       jb.out = reinterpret_cast<float4*>(ix->d_arena + pts_off[l]);
+      jb.cell_lo = slab ? (uint32_t)cell_lo : 0u;
+      jb.cell_hi = slab ? (uint32_t)cell_hi : 0xFFFFFFFFu;
       if (!(l == primary && primary_counted)) todo.l[todo.n++] = jb;
-      scan.in[l] = jb.counts;
-      scan.out[l] = ix->d_arena + cs_off[l];
-      scan.len[l] = cells_of(lg[l]);
+      scan.in[l] = jb.counts + (slab ? cell_lo : 0);
+      scan.out[l] = ix->d_arena + cs_off[l] + (slab ? cell_lo : 0);
+      scan.len[l] = slab ? cell_hi - cell_lo : cells_of(lg[l]);
     }
     const int grid = grid_for(ctx, n, kThreads);
     if (todo.n > 0) {
@@ -900,8 +980,35 @@ extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k
       zero.n[1] = primary_counted ? 0 : trial_words;
       k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all, zero);
       ctx->launches++;
-      if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "index build launch failed");
-      else restored = true;
+      trace.mark("launches: hist/scan/scatter");
+      if (slab) {
+        // table entries outside the slab (and the trial histogram's leftover counters there)
+        k_fill_outside<<<grid_for(ctx, cells_of(lg[0]), kThreads * 4), kThreads, 0, ctx->stream>>>(
+            ix->d_arena + cs_off[0], all.l[0].counts, cells_of(lg[0]), cell_lo, cell_hi);
+        ctx->launches++;
+        // the rank's own query range and point count, in local sorted positions
+        const uint32_t* cs = ix->d_arena + cs_off[0];
+        uint32_t* h = ctx->h_scratch + 44;
+        cudaMemcpyAsync(h + 0, cs + own_cell_lo, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h + 1, cs + own_cell_hi, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h + 2, cs + cell_hi, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        trace.mark("slab: fill + readback enqueued");
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+          st = tc_fail(ctx, TC_GPU, "sharded index build failed");
+        trace.mark("slab: stream sync");
+        ix->sharded = true;
+        ix->shard_halo = g_tc_shard_halo;
+        ix->cell_lo = cell_lo;
+        ix->cell_hi = cell_hi;
+        ix->own_cell_lo = own_cell_lo;
+        ix->own_cell_hi = own_cell_hi;
+        ix->own_lo = h[0];
+        ix->own_hi = h[1];
+        ix->n_local = h[2];
+      }
+      if (st == TC_OK && cudaGetLastError() != cudaSuccess)
+        st = tc_fail(ctx, TC_GPU, "index build launch failed");
+      else if (st == TC_OK) restored = true;
     }
   }
   tc_ws_release_zeroed(ctx, 1, d_tmp, restored);
@@ -961,7 +1068,24 @@ int tci_level0_max_population(tc_context* ctx, const tc_index* ix, uint32_t* out
 
 extern "C" void tc_index_free(tc_index* ix) {
   if (!ix) return;
-  tc_free(ix->ctx, ix->d_arena);  // the levels are views into the arena
+  // the levels are views into the arena; keep it for the next build when a slot is free (or
+  // holds a smaller one), else return it to the pool
+  tc_context* ctx = ix->ctx;
+  void* p = ix->d_arena;
+  uint64_t w = ix->arena_alloc_words;
+  if (p && w > 0) {
+    int slot = -1;
+    for (int a = 0; a < tc_context::kArenaSlots; ++a)
+      if (!ctx->arena_cache[a]) slot = a;
+    if (slot < 0)
+      for (int a = 0; a < tc_context::kArenaSlots; ++a)
+        if (ctx->arena_words[a] < w) slot = a;
+    if (slot >= 0) {
+      std::swap(p, ctx->arena_cache[slot]);
+      std::swap(w, ctx->arena_words[slot]);
+    }
+  }
+  tc_free(ctx, p);
   delete ix;
 }
 

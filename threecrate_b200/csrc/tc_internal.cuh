@@ -24,6 +24,12 @@ struct tc_context {
   uint32_t* h_scratch = nullptr;   // pinned + device-visible (UVA), 64 words: kernels publish small
                                    // results here and the host polls a sequence word
   uint32_t seq = 0;                // last sequence number handed to a publishing kernel
+  // index arenas handed back by tc_index_free, kept for the next build of a similar size: a
+  // cudaMallocAsync of a few hundred MB right after a stream synchronisation was measured at
+  // 0.5 - 50 ms of HOST time (the pool re-maps the block), which is the whole build time
+  static constexpr int kArenaSlots = 2;
+  void* arena_cache[kArenaSlots] = {nullptr, nullptr};
+  uint64_t arena_words[kArenaSlots] = {0, 0};
   bool stats_on = false;           // device counters of the search kernels (d_scratch[48..55])
   uint64_t stats_queries = 0;      // queries of the last search launch
   tc_stats icp_stats{};            // per-iteration history of the last ICP call (host copy)
@@ -51,6 +57,9 @@ struct GridParams {
   int nx, ny, nz;
   uint32_t n;           // points in the index
   int flags;            // search variant bits (see tc_search.cuh)
+  int ymajor;           // cell id = (cy nz + cz) nx + cx instead of (cz ny + cy) nx + cx: the axis
+                        // with more cells is the slowest one, so a contiguous range of the sorted
+                        // order is a slab along the long axis (multi-GPU shards: thin halos)
 };
 
 // One resolution of the index: a complete uniform grid over all points.
@@ -69,21 +78,38 @@ struct LevelSet {
   GridParams g[kMaxLevels];
   const float4* pts[kMaxLevels];
   const uint32_t* cs[kMaxLevels];
+  // slab-sharded index (tc_index_build_sharded): only the cells of the rank's slab +- `halo`
+  // planes hold points; a search whose final block radius exceeds the halo may have missed
+  // points of the unbuilt part and is counted in *unsafe (the caller then re-runs unsharded)
+  int halo;            // 0: complete index
+  uint32_t* unsafe;
 };
 
 struct tc_index {
   tc_context* ctx = nullptr;
   const tc_cloud* cloud = nullptr;  // borrowed; must outlive the index
   uint64_t n = 0;
+  uint64_t arena_alloc_words = 0;   // size of d_arena as allocated (may exceed what is used)
   float bbox_min[3]{}, bbox_max[3]{};
   int n_levels = 0;
   int primary = 0;                  // the level built for the requested / automatic cell size
   GridLevel lv[kMaxLevels];         // fine -> coarse; views into d_arena
   uint32_t* d_arena = nullptr;      // cell_start tables + sorted float4 points of every level
   mutable uint32_t level0_max_pop = 0;  // exact, lazily computed (tci_level0_max_population)
+  // slab-sharded build (multi-GPU normals): the index holds only the points of cells
+  // [cell_lo, cell_hi) = the rank's planes +- shard_halo; the rank OWNS the queries at sorted
+  // positions [own_lo, own_hi) (whole planes).  n_local = points held.
+  bool sharded = false;
+  int shard_rank = 0, shard_world = 1, shard_halo = 0;
+  uint64_t cell_lo = 0, cell_hi = 0, own_cell_lo = 0, own_cell_hi = 0;
+  uint64_t own_lo = 0, own_hi = 0, n_local = 0;
+  uint32_t k_hint = 0;
+  float cell_size_arg = 0.0f;
   LevelSet level_set(int flags) const {
     LevelSet s{};
     s.n = n_levels;
+    s.halo = sharded ? shard_halo : 0;
+    s.unsafe = sharded ? ctx->d_scratch + 42 : nullptr;
     for (int i = 0; i < n_levels; ++i) {
       s.g[i] = lv[i].g;
       s.g[i].flags = flags;
@@ -198,8 +224,12 @@ extern int g_tc_search_flags;  // default search variant (tc_debug_set_search_fl
 int tci_knn_launch(tc_context* ctx, const tc_index* index, const float4* d_queries_sorted,
                    uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out);
+// exact_range: [q_begin, q_end) are exactly the owned queries (no per-cell ownership test)
 int tci_normals_launch(tc_context* ctx, const tc_index* index, uint32_t k, int orient,
-                       const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos);
+                       const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos,
+                       bool exact_range = false);
+int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
+                    int rank, int world, tc_index** out);
 int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radius, uint32_t k,
                               int orient, const float vp[3], float* d_out_aos);
 int tci_radius_search_launch(tc_context* ctx, const tc_index* index, const float q[3], float radius,
@@ -267,6 +297,7 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv, int n, fl
   return c;
 }
 __device__ __forceinline__ uint32_t cell_id(const GridParams& g, int cx, int cy, int cz) {
-  return (uint32_t)(((int64_t)cz * g.ny + cy) * g.nx + cx);
+  return g.ymajor ? (uint32_t)(((int64_t)cy * g.nz + cz) * g.nx + cx)
+                  : (uint32_t)(((int64_t)cz * g.ny + cy) * g.nx + cx);
 }
 #endif

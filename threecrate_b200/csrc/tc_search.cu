@@ -31,11 +31,12 @@ template <int L, bool X>
 __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, float qy, float qz,
                                                uint32_t need, uint32_t (*s_a)[kBlock],
                                                uint32_t (*s_b)[kBlock], int& level,
-                                               uint32_t* dbg = nullptr) {
+                                               uint32_t* dbg = nullptr, int* R_out = nullptr) {
   constexpr int T = SelF<L, X>::kSlots;  // rows of s_a / s_b
   SelF<L, X> sel;
   sel.pad = T - (int)need;
   const int R = level_search(ls, qx, qy, qz, need, sel, level);
+  if (R_out) *R_out = R;
   const GridParams& g = ls.g[level];
   const float4* __restrict__ pts = ls.pts[level];
   const uint32_t* __restrict__ cell_start = ls.cs[level];
@@ -311,6 +312,7 @@ k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t
     TopK<K> tk;
     int level;
     const int R = level_search(ls, q.x, q.y, q.z, k + 1, tk, level);
+    if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
     normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
     if (dbg) {  // per-query cycles and final block radius (tools/qclock.py)
       dbg[8 * (size_t)qid] = (uint32_t)(clock64() - t0);
@@ -341,12 +343,13 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
     dbg[3] = (uint32_t)ns;
     dbg[7] = (uint32_t)t0;
   }
-  int level;
-  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, dbg);
+  int level, R = 0;
+  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, dbg, &R);
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
   }
+  if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
                out, (ls.g[0].flags & 128) != 0);
   if (dbg) {
@@ -554,7 +557,8 @@ k_normals_big(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint
   if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   HeapK hk{heaps + (uint64_t)t * (k + 1), k + 1, 0};
   int level;
-  level_search(ls, q.x, q.y, q.z, k + 1, hk, level);
+  const int R = level_search(ls, q.x, q.y, q.z, k + 1, hk, level);
+  if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);
   hk.sort_ascending();
   normals_emit(GlobalKeys{hk.h, (int)hk.n, xyz}, q, __float_as_uint(q.w), k, orient, vpx, vpy, vpz,
                out);
@@ -685,10 +689,11 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
 // Normals for the shard [q_begin, q_end) of the level-0 sorted order.  Shards own whole cells
 // (owns_query), so the launch covers up to max_pop extra positions past q_end.
 int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orient,
-                       const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos) {
+                       const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos,
+                       bool exact_range) {
   if (q_end <= q_begin) return TC_OK;
   const int sz = pick_size(k + 1);
-  const bool whole = (q_begin == 0 && q_end >= ix->n);
+  const bool whole = exact_range || (q_begin == 0 && q_end >= ix->n);
   const uint32_t own_begin = (uint32_t)q_begin;
   const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
   if (!whole) {  // cover every position of a cell that starts inside the shard (exact bound)
