@@ -81,13 +81,21 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz
     // four points = 48 bytes = three aligned 128-bit loads, all in flight together
     const float4* v4 = reinterpret_cast<const float4*>(xyz);
     const uint64_t groups = n / 4;
-    for (uint64_t gi = tid; gi < groups; gi += stride) {
-      const float4 a = v4[3 * gi], b = v4[3 * gi + 1], c = v4[3 * gi + 2];
+    auto four = [&](const float4& a, const float4& b, const float4& c) {
       upd(0, a.x); upd(1, a.y); upd(2, a.z);
       upd(0, a.w); upd(1, b.x); upd(2, b.y);
       upd(0, b.z); upd(1, b.w); upd(2, c.x);
       upd(0, c.y); upd(1, c.z); upd(2, c.w);
+    };
+    uint64_t gi = tid;
+    for (; gi + stride < groups; gi += 2 * stride) {  // six 128-bit loads in flight
+      const uint64_t gj = gi + stride;
+      const float4 a = v4[3 * gi], b = v4[3 * gi + 1], c = v4[3 * gi + 2];
+      const float4 d = v4[3 * gj], e = v4[3 * gj + 1], f = v4[3 * gj + 2];
+      four(a, b, c);
+      four(d, e, f);
     }
+    for (; gi < groups; gi += stride) four(v4[3 * gi], v4[3 * gi + 1], v4[3 * gi + 2]);
     done = 4 * groups;
   }
   for (uint64_t i = done + tid; i < n; i += stride) {
@@ -101,7 +109,30 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ xyz
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
   bad = __any_sync(0xffffffffu, bad);
+  // block-level reduction first: six atomics per BLOCK on six addresses (per warp they were the
+  // kernel's bottleneck: ~57k same-address atomics serialise in L2)
+  __shared__ float smn[kThreads / 32][3], smx[kThreads / 32][3];
+  __shared__ uint32_t sbad[kThreads / 32];
+  const int wid = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      smn[wid][a] = mn[a];
+      smx[wid][a] = mx[a];
+    }
+    sbad[wid] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = fminf(mn[a], smn[w][a]);
+        mx[a] = fmaxf(mx[a], smx[w][a]);
+      }
+      bad |= sbad[w];
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       if (mn[a] <= mx[a]) {
@@ -143,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(const float* __restrict_
 // once and its cell id recomputed per level (a dozen ALU ops; no key arrays, fewer launches).
 struct LevelJob {
   GridParams g;
+  int aggregate;               // warp-aggregate the atomics (tables with few cells per point)
   uint32_t* counts;            // n_cells + 1 (histogram, then scatter cursor)
   const uint32_t* cell_start;  // n_cells + 1 (scatter only)
   float4* out;                 // n (scatter only)
@@ -169,11 +201,15 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
     const uint32_t active = __activemask();
     for (int l = 0; l < jobs.n; ++l) {
       const uint32_t c = point_cell(jobs.l[l].g, x, y, z);
+      const bool in = c >= jobs.l[l].cell_lo && c < jobs.l[l].cell_hi;
+      if (!jobs.l[l].aggregate) {  // more cells than points: plain reductions, no matching
+        if (in) atomicAdd(&jobs.l[l].counts[c], 1u);
+        continue;
+      }
       // warp-aggregated: consecutive points of a scan usually share a cell, and coarse levels
       // funnel thousands of points into one counter
       const uint32_t peers = __match_any_sync(active, c);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && c >= jobs.l[l].cell_lo &&
-          c < jobs.l[l].cell_hi)
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && in)
         atomicAdd(&jobs.l[l].counts[c], (uint32_t)__popc(peers));
     }
   }
@@ -198,7 +234,15 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
   if ((reinterpret_cast<uintptr_t>(counts) & 15) == 0) {
     const uint4* c4 = reinterpret_cast<const uint4*>(counts);
     const uint64_t groups = n_cells / 4;
-    for (uint64_t gi = tid; gi < groups; gi += stride) {
+    uint64_t gi = tid;
+    for (; gi + 3 * stride < groups; gi += 4 * stride) {  // four 128-bit loads in flight
+      const uint4 a = c4[gi], b = c4[gi + stride], c = c4[gi + 2 * stride], d = c4[gi + 3 * stride];
+      upd(a.x); upd(a.y); upd(a.z); upd(a.w);
+      upd(b.x); upd(b.y); upd(b.z); upd(b.w);
+      upd(c.x); upd(c.y); upd(c.z); upd(c.w);
+      upd(d.x); upd(d.y); upd(d.z); upd(d.w);
+    }
+    for (; gi < groups; gi += stride) {
       const uint4 c = c4[gi];
       upd(c.x); upd(c.y); upd(c.z); upd(c.w);
     }
@@ -211,7 +255,22 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) low[j] += __shfl_xor_sync(0xffffffffu, low[j], o);
   }
+  __shared__ uint32_t sred[kThreads / 32][6];  // per-warp partials -> six atomics per block
   if ((threadIdx.x & 31) == 0) {
+    uint32_t* r = sred[threadIdx.x >> 5];
+    r[0] = occ;
+    r[1] = mx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[2 + j] = low[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) {
+      occ += sred[w][0];
+      mx = max(mx, sred[w][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) low[j] += sred[w][2 + j];
+    }
     if (occ) atomicAdd(&s[8], occ);
     if (mx) atomicMax(&s[9], mx);
 #pragma unroll
@@ -259,6 +318,11 @@ __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __rest
       const LevelJob& jb = jobs.l[l];
       const uint32_t c = point_cell(jb.g, x, y, z);
       // the histogram itself is the cursor: it counts down to zero while the cell fills up
+      if (!jb.aggregate) {  // more cells than points: one atomic per point, no matching
+        if (c >= jb.cell_lo && c < jb.cell_hi)
+          jb.out[__ldg(&jb.cell_start[c]) + atomicSub(&jb.counts[c], 1u) - 1u] = v;
+        continue;
+      }
       // (warp-aggregated: one atomic per distinct cell per warp)
       const uint32_t peers = __match_any_sync(active, c);
       const int leader = __ffs(peers) - 1;
@@ -546,12 +610,13 @@ int key_bits_for(uint64_t n_cells) {
 // ==========================================================================================
 // `d_state` (tiles + 1 u64 words, zeroed) may be supplied by the caller; otherwise it is
 // allocated and cleared here.
-// chunks per tile such that the largest table is cut into at most ~256 tiles
+// chunks per tile such that the largest table is cut into at most ~1024 tiles (every SM holds
+// several tiles in both phases; the look-back walks 32 tiles per step)
 static int scan_sub(const ScanJobs& jobs) {
   uint64_t longest = 0;
   for (int j = 0; j < jobs.n; ++j) longest = std::max(longest, jobs.len[j]);
   const uint64_t chunks = (longest + kScanTile - 1) / kScanTile;
-  return (int)std::min<uint64_t>(64, std::max<uint64_t>(1, (chunks + 255) / 256));
+  return (int)std::min<uint64_t>(64, std::max<uint64_t>(1, (chunks + 1023) / 1024));
 }
 static uint32_t scan_tiles(ScanJobs& jobs, int sub) {
   uint32_t tiles = 0;
@@ -736,6 +801,7 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   jobs.l[0].counts = d_counts;
   jobs.l[0].cell_lo = 0u;
   jobs.l[0].cell_hi = 0xFFFFFFFFu;
+  jobs.l[0].aggregate = n_cells < n ? 1 : 0;
   k_hist_levels<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n,
                                                                          jobs);
   TC_LAUNCHED(ctx);
@@ -957,6 +1023,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
       jb.counts = (l == primary && primary_counted) ? d_trial : d_tmp + cnt_off[l];
       jb.cell_start = ix->d_arena + cs_off[l];
       jb.out = reinterpret_cast<float4*>(ix->d_arena + pts_off[l]);
+      jb.aggregate = cells_of(lg[l]) < n ? 1 : 0;
       jb.cell_lo = slab ? (uint32_t)cell_lo : 0u;
       jb.cell_hi = slab ? (uint32_t)cell_hi : 0xFFFFFFFFu;
       if (!(l == primary && primary_counted)) todo.l[todo.n++] = jb;
