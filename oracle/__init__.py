@@ -33,6 +33,7 @@ from .oracle import (  # noqa: F401
     iso_apply,
     iso_mul,
     k_nearest_neighbors,
+    last_icp_mse_f64,
     max_threads,
     normals_f64,
     solve6,

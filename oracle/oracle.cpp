@@ -995,6 +995,12 @@ struct orc_icp_result {
   uint64_t n_corr;  // number of correspondence pairs written
 };
 
+// Diagnostic only (not part of the restated algorithm): the mean of the same f32 squared
+// residuals the reference sums, accumulated in f64 - tells how much of an mse difference is the
+// reference's own sequential-f32 accumulation error (5e-4 relative at 1M pairs).
+static double g_last_p2plane_mse_f64 = 0.0;
+double orc_last_icp_mse_f64() { return g_last_p2plane_mse_f64; }
+
 // icp_point_to_plane_detailed (registration.rs:508-602).
 // init7 = [tx,ty,tz, qi,qj,qk,qw].  max_dist < 0 => None.  pairs_out: capacity ns x 2 (u64).
 // Returns 0 OK, 1 InvalidData, 2 Algorithm.  OpenMP only over the correspondence search
@@ -1008,6 +1014,7 @@ int orc_icp_point_to_plane(const float* src, uint64_t ns, const float* tgt, uint
   if (max_iters == 0) return 1;      // :527-531
   Iso T{Quat{init7[3], init7[4], init7[5], init7[6]}, V3{init7[0], init7[1], init7[2]}};
   float previous_mse = INFINITY;
+  double previous_mse64 = 0.0;
   std::vector<std::pair<uint64_t, uint64_t>> final_corr;
   KdTree* tree = kd_new(tgt, nt);  // :536
   std::vector<V3> ts(ns);
@@ -1109,23 +1116,28 @@ int orc_icp_point_to_plane(const float* src, uint64_t ns, const float* tgt, uint
     T = iso_mul(delta, T);                                                  // :576
     // compute_point_to_plane_mse (:453-471) — residuals before delta
     float sum = 0.0f;
+    double sum64 = 0.0;
     for (size_t i = 0; i < vs.size(); ++i) {
       const V3 d{vt[i].x - vs[i].x, vt[i].y - vs[i].y, vt[i].z - vs[i].z};
       const float e = dot(vn[i], d);
       sum += e * e;
+      sum64 += (double)(e * e);
     }
     const float current_mse = sum / (float)vs.size();
     const float mse_change = std::fabs(previous_mse - current_mse);
     if (mse_change < conv) {  // :581-589
+      g_last_p2plane_mse_f64 = sum64 / (double)vs.size();
       finish(current_mse, iteration + 1, 1, corr_pairs);
       delete tree;
       return 0;
     }
     previous_mse = current_mse;
+    previous_mse64 = sum64 / (double)vs.size();
     final_corr = corr_pairs;
   }
   delete tree;
   if (status != 0) return status;
+  g_last_p2plane_mse_f64 = previous_mse64;
   finish(previous_mse, max_iters, 0, final_corr);  // :595-601
   return 0;
 }

@@ -246,6 +246,14 @@ def icp_point_to_plane(source, target, target_normals, init=None, max_iters: int
                      pairs[: res.n_corr].copy())
 
 
+def last_icp_mse_f64() -> float:
+    """Diagnostic: the last icp_point_to_plane call's mse with the SAME f32 squared residuals
+    accumulated in f64 (how far the reference's sequential f32 sum is from the exact mean)."""
+    lib = _load()
+    lib.orc_last_icp_mse_f64.restype = C.c_double
+    return float(lib.orc_last_icp_mse_f64())
+
+
 def icp_point_to_point(source, target, init=None, max_iters: int = 50, conv: float = 1e-6,
                        max_dist=None, threads: int = 0, validate_conv: bool = True) -> IcpResult:
     """icp_point_to_point (registration.rs:644-680) -> icp_detailed (:258-370)."""

@@ -39,6 +39,8 @@ extern "C" {
     fn tc_index_free(i: *mut TcIndex);
     fn tc_knn(ctx: *mut TcContext, ix: *const TcIndex, queries: *const f32, nq: u64, k: u32,
               exclude_self: c_int, idx: *mut u32, dist: *mut f32, count: *mut u32) -> c_int;
+    fn tc_radius_search(ctx: *mut TcContext, ix: *const TcIndex, query: *const f32, radius: f32,
+                        idx: *mut u32, dist: *mut f32, capacity: u64, n_found: *mut u64) -> c_int;
     fn tc_estimate_normals(ctx: *mut TcContext, xyz: *const f32, n: u64, k: u32, radius: f32,
                            consistent: c_int, viewpoint: *const f32, out: *mut f32) -> c_int;
     fn tc_icp_point_to_plane(ctx: *mut TcContext, src: *const f32, ns: u64, tgt: *const f32, nt: u64,
@@ -116,6 +118,19 @@ pub fn estimate_normals_with_config(points: &[Point3f], k: usize, radius: Option
     Ok(PointCloud::from_points(out))
 }
 
+/// Drop-in for `estimate_normals(&cloud, k)` (normals.rs:238-247): defaults of
+/// `NormalEstimationConfig` (no radius, consistent orientation, bbox-derived viewpoint).
+pub fn estimate_normals(points: &[Point3f], k: usize) -> Result<PointCloud<NormalPoint3f>> {
+    estimate_normals_with_config(points, k, None, true, None)
+}
+
+/// Drop-in for `estimate_normals_radius(&cloud, radius, consistent)` (normals.rs:368-380):
+/// `k_neighbors = 10` is the value the reference passes as the fallback count.
+pub fn estimate_normals_radius(points: &[Point3f], radius: f32, consistent_orientation: bool)
+                               -> Result<PointCloud<NormalPoint3f>> {
+    estimate_normals_with_config(points, 10, Some(radius), consistent_orientation, None)
+}
+
 /// Device-backed stand-in for `KdTree` (nearest_neighbor.rs:29): build once, query many.
 pub struct CudaKdTree { cloud: *mut TcCloud, index: *mut TcIndex, len: usize }
 
@@ -139,6 +154,18 @@ impl CudaKdTree {
         })).expect("tc_knn");
         (0..cnt[0] as usize).map(|j| (idx[j] as usize, dist[j])).collect()
     }
+    /// `NearestNeighborSearch::find_radius_neighbors` (traits.rs:6-12; nearest_neighbor.rs:254-298):
+    /// every point with d2 <= radius^2, ascending by distance; radius <= 0 finds nothing.
+    pub fn find_radius_neighbors(&self, query: &Point3f, radius: f32) -> Vec<(usize, f32)> {
+        if !(radius > 0.0) || self.len == 0 { return Vec::new(); }
+        let q = [query.x, query.y, query.z];
+        let (mut idx, mut dist, mut found) = (vec![0u32; self.len], vec![0f32; self.len], 0u64);
+        CTX.with(|c| c.check(unsafe {
+            tc_radius_search(c.0, self.index, q.as_ptr(), radius, idx.as_mut_ptr(), dist.as_mut_ptr(),
+                             self.len as u64, &mut found)
+        })).expect("tc_radius_search");
+        (0..(found as usize).min(self.len)).map(|j| (idx[j] as usize, dist[j])).collect()
+    }
     /// `PointCloudNeighbors::k_nearest_neighbors` (point_cloud_ops.rs:80-105).
     pub fn k_nearest_neighbors(&self, k: usize) -> Vec<Vec<(usize, f32)>> {
         if k == 0 || self.len == 0 { return Vec::new(); }
@@ -151,6 +178,17 @@ impl CudaKdTree {
     }
 }
 impl Drop for CudaKdTree { fn drop(&mut self) { unsafe { tc_index_free(self.index); tc_cloud_free(self.cloud) } } }
+
+/// The trait the reference's generic callers use (`threecrate-core/src/traits.rs:6-12`), so a
+/// `CudaKdTree` can stand wherever a `KdTree` is passed as `&dyn NearestNeighborSearch`.
+impl threecrate_core::NearestNeighborSearch for CudaKdTree {
+    fn find_k_nearest(&self, query: &Point3f, k: usize) -> Vec<(usize, f32)> {
+        CudaKdTree::find_k_nearest(self, query, k)
+    }
+    fn find_radius_neighbors(&self, query: &Point3f, radius: f32) -> Vec<(usize, f32)> {
+        CudaKdTree::find_radius_neighbors(self, query, radius)
+    }
+}
 
 /// Mirror of `threecrate_algorithms::ICPResult` fields (registration.rs:13-24).
 pub struct IcpOut {
@@ -202,9 +240,24 @@ fn icp_out(res: &TcIcpResult, pairs: &[u64]) -> IcpOut {
     }
 }
 
-/// Drop-in for `icp_detailed` / `icp_point_to_point` (registration.rs:258, 644).
+/// Drop-in for `icp_detailed` (registration.rs:258): no check of the threshold's sign.
+pub fn icp_detailed(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>, max_iters: usize,
+                    max_dist: Option<f32>, conv: f32) -> Result<IcpOut> {
+    icp_point_to_point_unchecked(source, target, init, max_iters, conv, max_dist)
+}
+
+/// Drop-in for `icp_point_to_point` (registration.rs:644-680), including its own validation:
+/// `convergence_threshold <= 0` is `InvalidData` there (:665-669) before anything runs.
 pub fn icp_point_to_point(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>,
                           max_iters: usize, conv: f32, max_dist: Option<f32>) -> Result<IcpOut> {
+    if conv <= 0.0 {
+        return Err(Error::InvalidData("Convergence threshold must be positive".into()));
+    }
+    icp_point_to_point_unchecked(source, target, init, max_iters, conv, max_dist)
+}
+
+fn icp_point_to_point_unchecked(source: &[Point3f], target: &[Point3f], init: Isometry3<f32>,
+                                max_iters: usize, conv: f32, max_dist: Option<f32>) -> Result<IcpOut> {
     let init7 = iso7(&init);
     let mut res = TcIcpResult::default();
     let mut pairs = vec![0u64; 2 * source.len().max(1)];

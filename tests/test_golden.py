@@ -84,3 +84,68 @@ def test_gpu_filters_match_golden():
     got, st = tc.statistical_outlier_removal(f, 8, 1.0, return_stats=True)
     assert np.array_equal(got, f[G["sor_k8_mask"]])
     assert np.array_equal(np.float32([st["mean"], st["std_dev"], st["threshold"]]), G["sor_k8_stats"])
+
+
+# ------------------------------------------------------------------------------------------
+# Reference-pinned vectors: produced by rust/golden_dumper/dump_golden.rs INSIDE the reference
+# checkout (needs cargo, absent from the build image).  Until tests/golden/reference_v1.bin is
+# committed these tests skip and parity stays "unpinned"; once it exists they hold BOTH the
+# oracle restatement and the CUDA path to the reference's real output.
+# ------------------------------------------------------------------------------------------
+_REF = os.path.join(HERE, "golden", "reference_v1.bin")
+_need_ref = pytest.mark.skipif(not os.path.exists(_REF),
+                               reason="parity unpinned: tests/golden/reference_v1.bin not generated yet "
+                                      "(run rust/golden_dumper/dump_golden.rs in the reference checkout)")
+
+
+def _load_ref():
+    spec = importlib.util.spec_from_file_location(
+        "make_reference_inputs", os.path.join(HERE, "golden", "make_reference_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.read_reference(_REF), mod.CASES
+
+
+def _check_against_reference(knn_fn, normals_fn, icp_fn):
+    ref, cases = _load_ref()
+    for r, c in zip(ref, cases):
+        if r["kind"] == 1:
+            pts, k = c[2], r["k"]
+            idx, dist = knn_fn(pts, k + 1)
+            # canonical (d2, index) order on both sides; exact wherever the distances are distinct
+            distinct = np.all(np.diff(r["dist"], axis=1) > 0, axis=1)
+            assert np.array_equal(idx[distinct].astype(np.uint64), r["idx"][distinct])
+            assert np.array_equal(dist[distinct], r["dist"][distinct])
+            got = normals_fn(pts, k)
+            a, b = got[:, 3:].astype(np.float64), r["normals"][:, 3:].astype(np.float64)
+            ang = np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), (a * b).sum(1))
+            assert np.percentile(ang, 99) <= 1e-4
+        else:
+            got = icp_fn(c[2], c[3], c[4], c[5])
+            assert np.linalg.norm(got.translation.astype(np.float64) - r["T"][:3]) <= 1e-5
+            assert _quat_angle(got.rotation, r["T"][3:]) <= 1e-5
+            assert got.iterations == r["iterations"] and got.converged == r["converged"]
+
+
+@_need_ref
+def test_oracle_matches_reference_pinned_vectors():
+    import oracle
+
+    def knn(pts, k):
+        i, d2 = oracle.brute_knn(pts, pts, k)
+        return i, np.sqrt(d2)
+    _check_against_reference(knn, oracle.estimate_normals,
+                             lambda s, t, n, it: oracle.icp_point_to_plane(s, t, n, max_iters=it, conv=-1.0))
+
+
+@_need_ref
+@pytest.mark.gpu
+def test_gpu_matches_reference_pinned_vectors():
+    import threecrate_b200 as tc
+
+    def knn(pts, k):
+        i, d, _ = tc.KdTree(pts, k_hint=k).knn(pts, k)
+        return i, d
+    _check_against_reference(knn, tc.estimate_normals,
+                             lambda s, t, n, it: tc.icp_point_to_plane_detailed(s, t, n, tc.IDENTITY, it,
+                                                                                None, -1.0))

@@ -43,6 +43,9 @@ struct IcpState {
   int32_t done;
   uint32_t ticket;     // block completion counter
   double n_valid;
+  // per-iteration history for tc_last_stats (first TC_STATS_MAX_ITERS iterations)
+  float mse_hist[TC_STATS_MAX_ITERS];
+  double valid_hist[TC_STATS_MAX_ITERS];
 };
 
 struct V3 {
@@ -373,11 +376,32 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
   __syncthreads();
   if (last) {
     __threadfence();
+    // Block partials -> totals with the whole block: warp w takes blocks w, w+8, ... (lane j =
+    // sum j, four independent accumulators so the L2 loads overlap), the eight slices are then
+    // added in warp order.  The association is fixed by (gridDim, block size) alone, so the
+    // result does not depend on scheduling.  (Walking all blocks with 29 threads in one dependent
+    // chain was most of the per-iteration tail: ~600 L2 round trips.)
     double v = 0.0;
-    if (threadIdx.x < NS) {
-      for (uint32_t b = 0; b < gridDim.x; ++b)
-        v += __ldcg(&partials[(uint64_t)b * NS + threadIdx.x]);
-      sums[threadIdx.x] = v;
+    {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (lane < NS) {
+        uint32_t b = warp;
+        for (; b + 24 < gridDim.x; b += 32) {
+          a0 += __ldcg(&partials[(uint64_t)b * NS + lane]);
+          a1 += __ldcg(&partials[(uint64_t)(b + 8) * NS + lane]);
+          a2 += __ldcg(&partials[(uint64_t)(b + 16) * NS + lane]);
+          a3 += __ldcg(&partials[(uint64_t)(b + 24) * NS + lane]);
+        }
+        for (; b < gridDim.x; b += 8) a0 += __ldcg(&partials[(uint64_t)b * NS + lane]);
+      }
+      __syncthreads();  // sm[][] was read by the first NS threads above
+      sm[warp][lane] = (a0 + a1) + (a2 + a3);
+      __syncthreads();
+      if (threadIdx.x < NS) {
+#pragma unroll
+        for (int w = 0; w < kIcpBlock / 32; ++w) v += sm[w][threadIdx.x];
+        sums[threadIdx.x] = v;
+      }
     }
     if (threadIdx.x == 0) st->ticket = 0;
     if (fuse && px.world > 1) {
@@ -570,6 +594,10 @@ __device__ void icp_apply_delta(IcpState* st, const float dq[4], const float dt[
   st->T[4] = qn[1];
   st->T[5] = qn[2];
   st->T[6] = qn[3];
+  if (st->iterations < TC_STATS_MAX_ITERS) {
+    st->mse_hist[st->iterations] = mse;
+    st->valid_hist[st->iterations] = st->n_valid;
+  }
   st->iterations += 1;
   st->mse = mse;
   if (fabsf(st->prev_mse - mse) < conv) {
@@ -724,6 +752,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
                     float max_corr_dist, float conv_threshold, tc_icp_result* out,
                     uint32_t* d_match_out) {
   if (!ctx || !src || !tgt || !out || !init) return TC_INVALID_DATA;
+  TcRange nvtx_range(mode == kPlane ? "tc:icp point-to-plane" : mode == kPoint ? "tc:icp point-to-point" : "tc:gicp");
   // validation order of registration.rs:266-276 / 517-531 (normals length: host wrapper)
   if (tgt->sharded)
     return tc_fail(ctx, TC_INVALID_DATA, "ICP needs a complete target index (not a slab-sharded one)");
@@ -870,6 +899,14 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
     return tc_fail(ctx, TC_ALGORITHM, mode == kPlane  ? "Point-to-plane system is ill-conditioned"
                                       : mode == kGicp ? "GICP: Gauss-Newton system is ill-conditioned"
                                                       : "SVD of the cross-covariance failed");
+  {  // per-iteration history (tc_last_stats)
+    tc_stats& hs = ctx->icp_stats;
+    hs.icp_iterations = std::min<uint32_t>(h_state.iterations, TC_STATS_MAX_ITERS);
+    for (uint32_t i = 0; i < TC_STATS_MAX_ITERS; ++i) {
+      hs.icp_mse[i] = i < hs.icp_iterations ? h_state.mse_hist[i] : 0.0f;
+      hs.icp_valid[i] = i < hs.icp_iterations ? (uint64_t)h_state.valid_hist[i] : 0;
+    }
+  }
   for (int i = 0; i < 7; ++i) out->transform[i] = h_state.T[i];
   if (h_state.converged) {
     out->mse = h_state.mse;

@@ -724,6 +724,7 @@ static int wait_host_flag(tc_context* ctx, volatile uint32_t* flag, uint32_t seq
 }
 
 int tci_bbox(tc_context* ctx, const float* d_xyz, uint64_t n, float mn[3], float mx[3]) {
+  TcRange nvtx_range("tc:bbox");
   const uint32_t seq = ++ctx->seq;
   k_bbox<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(d_xyz, n, ctx->d_scratch,
                                                                       ctx->h_scratch, seq);
@@ -838,6 +839,7 @@ extern "C" int tc_index_build_sharded(tc_context* ctx, const tc_cloud* cloud, ui
 
 int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
                     int rank, int world, tc_index** out) {
+  TcRange nvtx_range("tc_index_build");
   if (!ctx || !cloud || !out) return TC_INVALID_DATA;
   *out = nullptr;
   const uint64_t n = cloud->n;
@@ -1179,6 +1181,7 @@ extern "C" int tc_index_get_info(const tc_index* ix, tc_index_info* out) {
 // threads walk neighbouring cells.  Key = clamped cell id in g.
 int tci_sort_by_grid(tc_context* ctx, const float* d_xyz, uint64_t n, const GridParams& g,
                      float4** d_sorted) {
+  TcRange nvtx_range("tc:sort_by_grid (radix)");
   *d_sorted = nullptr;
   if (n == 0) return TC_OK;
   uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_vals = nullptr, *d_vals_alt = nullptr;

@@ -123,6 +123,18 @@ struct tc_index {
 struct tc_comm;  // tc_comm.cu
 
 // ------------------------------------------------------------------------------------------
+// NVTX ranges per phase (SURVEY §5 tracing): header-only nvtx3, a no-op unless a profiler
+// (nsys / ncu --nvtx) is attached
+// ------------------------------------------------------------------------------------------
+#include <nvtx3/nvToolsExt.h>
+struct TcRange {
+  explicit TcRange(const char* name) { nvtxRangePushA(name); }
+  ~TcRange() { nvtxRangePop(); }
+  TcRange(const TcRange&) = delete;
+  TcRange& operator=(const TcRange&) = delete;
+};
+
+// ------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------
 inline int tc_fail(tc_context* ctx, int status, const std::string& msg) {

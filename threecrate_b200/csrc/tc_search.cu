@@ -618,6 +618,7 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
                    uint64_t q_begin, uint64_t q_end, uint32_t k, int exclude_self, bool self_query,
                    uint32_t* d_idx_out, float* d_dist_out, uint32_t* d_count_out) {
   if (q_end <= q_begin) return TC_OK;
+  TcRange nvtx_range("tc:knn");
   const int drop_self = (exclude_self && self_query) ? 1 : 0;
   const uint32_t need = k + (drop_self ? 1u : 0u);
   const int sz = pick_size(need);
@@ -692,6 +693,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
                        const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos,
                        bool exact_range) {
   if (q_end <= q_begin) return TC_OK;
+  TcRange nvtx_range("tc:normals");
   const int sz = pick_size(k + 1);
   const bool whole = exact_range || (q_begin == 0 && q_end >= ix->n);
   const uint32_t own_begin = (uint32_t)q_begin;
