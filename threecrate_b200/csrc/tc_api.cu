@@ -500,9 +500,11 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
     default_viewpoint(ix->bbox_min, ix->bbox_max, vp);
   }
   if (radius > 0.0f) {  // Some(radius); radius <= 0 finds nothing and is the kNN rule for everyone
-    if (shard_begin != 0 || shard_end < ix->n || ix->sharded)
-      return tc_fail(ctx, TC_INVALID_DATA, "radius-mode normals are not sharded; pass the full range");
-    return tci_normals_radius_launch(ctx, ix, radius, k, consistent_orientation ? 1 : 0, vp, d_out_aos);
+    if (ix->sharded)
+      return tc_fail(ctx, TC_INVALID_DATA,
+                     "radius-mode normals need a complete index (shard by sorted range instead)");
+    return tci_normals_radius_launch(ctx, ix, radius, k, consistent_orientation ? 1 : 0, vp,
+                                     shard_begin, shard_end, d_out_aos);
   }
   if (!ix->sharded)
     return tci_normals_launch(ctx, ix, k, consistent_orientation ? 1 : 0, vp, shard_begin, shard_end,

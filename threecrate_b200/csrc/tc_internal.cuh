@@ -243,7 +243,8 @@ int tci_normals_launch(tc_context* ctx, const tc_index* index, uint32_t k, int o
 int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
                     int rank, int world, tc_index** out);
 int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radius, uint32_t k,
-                              int orient, const float vp[3], float* d_out_aos);
+                              int orient, const float vp[3], uint64_t q_begin, uint64_t q_end,
+                              float* d_out_aos);
 int tci_radius_search_launch(tc_context* ctx, const tc_index* index, const float q[3], float radius,
                              uint32_t* d_idx, float* d_d2, uint32_t capacity, uint32_t* d_count);
 

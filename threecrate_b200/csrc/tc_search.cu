@@ -360,66 +360,117 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
 
 // ------------------------------------------------------------------------------ radius mode
 // estimate_normals_with_config with radius = Some(r) (normals.rs:141-146, 315-340): neighbourhood
-// = every point with d2 <= r^2 except the query's own index, then the query itself.  Queries with
-// fewer than k such neighbours fall back to the kNN rule (appended to `fb_list`, finished by the
-// chain kernel).  The reference sums the neighbours in ascending-distance order in f32; here the
-// sums run in scan order but in f64 and are rounded to f32 once (the difference is the
-// reference's own f32 accumulation error).
+// = every point with d2 <= r^2 except the query's own index, in ascending-distance order
+// (find_radius_neighbors sorts, nearest_neighbor.rs:283-296), then the query itself; the sums are
+// sequential f32 in that order (normals.rs:165-177).  Queries with fewer than k such neighbours
+// fall back to the kNN rule (normals.rs:315-323): appended to `fb_list`.
+// Three steps so that every query can hold ALL its neighbours (a radius has no upper bound on
+// their number): count -> exclusive scan -> fill + in-place heapsort of the query's own segment
+// of u64 (d2 bits << 32 | index) keys + the reference-order sums.
 __global__ void __launch_bounds__(kBlock)
-k_normals_radius(LevelSet ls, int level, uint32_t n, float radius, uint32_t k, int orient, float vpx,
-                 float vpy, float vpz, float* __restrict__ out, uint32_t* __restrict__ fb_list,
-                 uint32_t* __restrict__ fb_count) {
-  const uint32_t qi = blockIdx.x * kBlock + threadIdx.x;
-  if (qi >= n) return;
+k_radius_count(LevelSet ls, int level, uint32_t q_begin, uint32_t q_end, uint32_t own_begin,
+               uint32_t own_end, float radius, uint32_t k, uint32_t* __restrict__ counts,
+               uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+  const uint32_t qi = q_begin + t;
+  if (qi >= q_end) return;
+  counts[t] = 0u;
   const float4 q = __ldg(&ls.pts[0][qi]);
+  if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   const uint32_t qid = __float_as_uint(q.w);
-  const GridParams& g = ls.g[level];
   const float4* __restrict__ pts = ls.pts[level];
   const float r2 = xmul(radius, radius);  // nearest_neighbor.rs:259
   uint32_t cnt = 0;
-  double sx = 0, sy = 0, sz = 0;
-  box_visit(g, ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
+  box_visit(ls.g[level], ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t j = lo; j < hi; ++j) {
       const float4 c = __ldg(&pts[j]);
       const float d2 = dist2_exact(c.x, c.y, c.z, q.x, q.y, q.z);
-      if (d2 <= r2 && __float_as_uint(c.w) != qid) {
-        ++cnt;
-        sx += c.x;
-        sy += c.y;
-        sz += c.z;
-      }
+      if (d2 <= r2 && __float_as_uint(c.w) != qid) ++cnt;
     }
   });
-  if (cnt < k) {  // normals.rs:315-323
+  if (cnt < k) {  // normals.rs:315-323: the kNN rule instead
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
   }
-  const uint32_t nn = cnt + 1;  // + the query itself (normals.rs:338-340)
-  const float fn = (float)nn;
-  const float cx = (float)((sx + q.x) / (double)nn), cy = (float)((sy + q.y) / (double)nn),
-              cz = (float)((sz + q.z) / (double)nn);
-  double m[6] = {0, 0, 0, 0, 0, 0};
-  auto acc = [&](float px, float py, float pz) {
-    const double dx = (double)xsub(px, cx), dy = (double)xsub(py, cy), dz = (double)xsub(pz, cz);
-    m[0] += dx * dx;
-    m[1] += dx * dy;
-    m[2] += dx * dz;
-    m[3] += dy * dy;
-    m[4] += dy * dz;
-    m[5] += dz * dz;
-  };
-  box_visit(g, ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
+  counts[t] = cnt;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_radius_normals(LevelSet ls, int level, const float* __restrict__ xyz, uint32_t q_begin,
+                 uint32_t q_end, float radius, int orient, float vpx, float vpy, float vpz,
+                 const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
+                 float* __restrict__ out) {
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+  const uint32_t qi = q_begin + t;
+  if (qi >= q_end) return;
+  const uint32_t n = offsets[t + 1] - offsets[t];
+  if (n == 0) return;  // not owned, or left to the kNN rule
+  const float4 q = __ldg(&ls.pts[0][qi]);
+  const uint32_t qid = __float_as_uint(q.w);
+  const float4* __restrict__ pts = ls.pts[level];
+  const float r2 = xmul(radius, radius);
+  uint64_t* h = keys + offsets[t];
+  uint32_t m = 0;
+  box_visit(ls.g[level], ls.cs[level], q.x, q.y, q.z, r2, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t j = lo; j < hi; ++j) {
       const float4 c = __ldg(&pts[j]);
       const float d2 = dist2_exact(c.x, c.y, c.z, q.x, q.y, q.z);
-      if (d2 <= r2 && __float_as_uint(c.w) != qid) acc(c.x, c.y, c.z);
+      const uint32_t id = __float_as_uint(c.w);
+      if (d2 <= r2 && id != qid && m < n) h[m++] = ((uint64_t)__float_as_uint(d2) << 32) | id;
     }
   });
+  // in-place heapsort -> ascending (d2, index)
+  auto sift = [&](uint32_t i, uint32_t end, uint64_t v) {
+    while (true) {
+      uint32_t c = 2 * i + 1;
+      if (c >= end) break;
+      if (c + 1 < end && h[c + 1] > h[c]) ++c;
+      if (h[c] <= v) break;
+      h[i] = h[c];
+      i = c;
+    }
+    h[i] = v;
+  };
+  for (uint32_t i = m / 2; i-- > 0;) sift(i, m, h[i]);
+  for (uint32_t end = m; end > 1; --end) {
+    const uint64_t last = h[end - 1];
+    h[end - 1] = h[0];
+    sift(0, end - 1, last);
+  }
+  // reference-order sums (normals.rs:165-177): neighbours ascending, the query itself last
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  for (uint32_t i = 0; i < m; ++i) {
+    const float* p = xyz + 3 * (uint64_t)(uint32_t)h[i];
+    sx = xadd(sx, __ldg(p));
+    sy = xadd(sy, __ldg(p + 1));
+    sz = xadd(sz, __ldg(p + 2));
+  }
+  sx = xadd(sx, q.x);
+  sy = xadd(sy, q.y);
+  sz = xadd(sz, q.z);
+  const float fn = (float)(m + 1);
+  const float cx = xdiv(sx, fn), cy = xdiv(sy, fn), cz = xdiv(sz, fn);
+  float c[6] = {0, 0, 0, 0, 0, 0};
+  auto acc = [&](float px, float py, float pz) {
+    const float dx = xsub(px, cx), dy = xsub(py, cy), dz = xsub(pz, cz);
+    c[0] = xadd(c[0], xmul(dx, dx));
+    c[1] = xadd(c[1], xmul(dx, dy));
+    c[2] = xadd(c[2], xmul(dx, dz));
+    c[3] = xadd(c[3], xmul(dy, dy));
+    c[4] = xadd(c[4], xmul(dy, dz));
+    c[5] = xadd(c[5], xmul(dz, dz));
+  };
+  for (uint32_t i = 0; i < m; ++i) {
+    const float* p = xyz + 3 * (uint64_t)(uint32_t)h[i];
+    acc(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+  }
   acc(q.x, q.y, q.z);
-  float cov[6], nrm[3];
+  float nrm[3] = {0.0f, 0.0f, 1.0f};
+  if (m + 1 >= 3) {  // normals.rs:159-162
 #pragma unroll
-  for (int i = 0; i < 6; ++i) cov[i] = xdiv((float)m[i], fn);
-  normal_from_cov(cov, nrm);
+    for (int i = 0; i < 6; ++i) c[i] = xdiv(c[i], fn);
+    normal_from_cov(c, nrm, (ls.g[0].flags & 128) != 0);
+  }
   write_normal(nrm, q, qid, orient, vpx, vpy, vpz, out);
 }
 
@@ -547,14 +598,16 @@ k_knn_big(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uin
            dist_out, count_out);
 }
 
+// (`list` != nullptr: the query positions list[q_begin .. q_end) instead of the range itself)
 __global__ void __launch_bounds__(kBlock)
 k_normals_big(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end,
               uint32_t own_begin, uint32_t own_end, uint32_t k, int orient, float vpx, float vpy,
-              float vpz, float* __restrict__ out, uint64_t* __restrict__ heaps) {
+              float vpz, float* __restrict__ out, uint64_t* __restrict__ heaps,
+              const uint32_t* __restrict__ list = nullptr) {
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
   if (t >= q_end - q_begin) return;
-  const float4 q = __ldg(&ls.pts[0][q_begin + t]);
-  if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
+  const float4 q = __ldg(&ls.pts[0][list ? list[q_begin + t] : q_begin + t]);
+  if (!list && own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   HeapK hk{heaps + (uint64_t)t * (k + 1), k + 1, 0};
   int level;
   const int R = level_search(ls, q.x, q.y, q.z, k + 1, hk, level);
@@ -768,33 +821,93 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   return TC_OK;
 }
 
-// Radius-mode normals for the whole cloud (no sharding of this mode yet).
+// Radius-mode normals for the shard [q_begin, q_end) of the level-0 sorted order (whole cells are
+// owned, as in tci_normals_launch).  Queries are taken a chunk at a time so the key segments of a
+// chunk fit a bounded buffer.
 int tci_normals_radius_launch(tc_context* ctx, const tc_index* ix, float radius, uint32_t k,
-                              int orient, const float vp[3], float* d_out_aos) {
-  const uint32_t n = (uint32_t)ix->n;
-  if (n == 0) return TC_OK;
-  const int sz = pick_size(k + 1);
-  if (sz == 0)
-    return tc_fail(ctx, TC_INVALID_DATA, "k too large for the device top-k (max 63 for normals)");
+                              int orient, const float vp[3], uint64_t q_begin, uint64_t q_end,
+                              float* d_out_aos) {
+  if (q_end <= q_begin || ix->n == 0) return TC_OK;
+  TcRange nvtx_range("tc:normals (radius)");
+  const bool whole = (q_begin == 0 && q_end >= ix->n);
+  const uint32_t own_begin = (uint32_t)q_begin;
+  const uint32_t own_end = whole ? 0xFFFFFFFFu : (uint32_t)q_end;
+  if (!whole) {
+    uint32_t max_pop = 0;
+    TC_TRY(tci_level0_max_population(ctx, ix, &max_pop));
+    q_end = std::min<uint64_t>(ix->n, q_end + max_pop);
+  }
   const LevelSet ls = ix->level_set(g_tc_search_flags | 2);
   // the level whose cell edge is closest to (and not far below) the radius keeps the box small
   int level = 0;
   for (int l = 0; l < ix->n_levels; ++l)
     if (ix->lv[l].g.cell <= 2.0f * radius) level = l;
-  uint32_t* d_fb = nullptr;
-  TC_TRY(tc_alloc(ctx, &d_fb, (uint64_t)n + 1));
-  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
-  const dim3 grid((n + kBlock - 1) / kBlock);
-  k_normals_radius<<<grid, kBlock, 0, ctx->stream>>>(ls, level, n, radius, k, orient, vp[0], vp[1],
-                                                     vp[2], d_out_aos, d_fb + 1, d_fb);
-  TC_LAUNCHED(ctx);
-  const dim3 fgrid(std::min<uint32_t>(grid.x, (uint32_t)ctx->sm_count * 4));
-  TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
-                        ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],
-                        d_out_aos, d_fb + 1, d_fb, nullptr)));
-  TC_LAUNCHED(ctx);
+  const uint32_t nq = (uint32_t)(q_end - q_begin);
+  constexpr uint32_t kChunk = 1u << 20;
+  const uint32_t chunk = std::min(nq, kChunk);
+  uint32_t *d_fb = nullptr, *d_cnt = nullptr;
+  int st = tc_alloc(ctx, &d_fb, (uint64_t)nq + 1);
+  if (st == TC_OK) st = tc_alloc(ctx, &d_cnt, (uint64_t)chunk + 1);
+  if (st == TC_OK && cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess)
+    st = tc_fail(ctx, TC_GPU, "radius normals: memset failed");
+  for (uint64_t b = q_begin; b < q_end && st == TC_OK; b += chunk) {
+    const uint32_t e = (uint32_t)std::min<uint64_t>(q_end, b + chunk), m = e - (uint32_t)b;
+    const dim3 grid((m + kBlock - 1) / kBlock);
+    k_radius_count<<<grid, kBlock, 0, ctx->stream>>>(ls, level, (uint32_t)b, e, own_begin, own_end,
+                                                     radius, k, d_cnt, d_fb + 1, d_fb);
+    ctx->launches++;
+    st = tci_exclusive_scan_u32(ctx, d_cnt, d_cnt, m);  // d_cnt[m] = total keys of the chunk
+    uint32_t total = 0;
+    if (st == TC_OK) {
+      cudaError_t err = cudaMemcpyAsync(&total, d_cnt + m, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                        ctx->stream);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+      if (err != cudaSuccess) st = tc_fail(ctx, TC_GPU, "radius normals: count readback failed");
+    }
+    if (st != TC_OK || total == 0) continue;
+    uint64_t* d_keys = nullptr;
+    st = tc_alloc(ctx, &d_keys, total);
+    if (st == TC_OK) {
+      k_radius_normals<<<grid, kBlock, 0, ctx->stream>>>(ls, level, ix->cloud->d_xyz, (uint32_t)b, e,
+                                                         radius, orient, vp[0], vp[1], vp[2], d_cnt,
+                                                         d_keys, d_out_aos);
+      ctx->launches++;
+    }
+    tc_free(ctx, d_keys);
+  }
+  // queries with fewer than k neighbours in the radius: the kNN rule, any k
+  uint32_t n_fb = 0;
+  if (st == TC_OK) {
+    cudaError_t err = cudaMemcpyAsync(&n_fb, d_fb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess) st = tc_fail(ctx, TC_GPU, "radius normals: fallback readback failed");
+  }
+  if (st == TC_OK && n_fb > 0) {
+    const int sz = pick_size(k + 1);
+    if (sz != 0) {
+      const dim3 fgrid(std::min<uint32_t>((n_fb + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count * 4));
+      TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
+                            ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1],
+                            vp[2], d_out_aos, d_fb + 1, d_fb, nullptr)));
+      ctx->launches++;
+    } else {  // k + 1 beyond the register lists: global-memory heaps over the list, in chunks
+      const uint32_t hchunk = std::min(n_fb, kBigChunk);
+      uint64_t* d_heaps = nullptr;
+      st = tc_alloc(ctx, &d_heaps, (uint64_t)hchunk * (k + 1));
+      for (uint32_t b = 0; b < n_fb && st == TC_OK; b += hchunk) {
+        const uint32_t e = std::min(n_fb, b + hchunk);
+        k_normals_big<<<(e - b + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(
+            ls, ix->cloud->d_xyz, b, e, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2], d_out_aos,
+            d_heaps, d_fb + 1);
+        ctx->launches++;
+      }
+      tc_free(ctx, d_heaps);
+    }
+    if (cudaGetLastError() != cudaSuccess) st = tc_fail(ctx, TC_GPU, "radius normals launch failed");
+  }
+  tc_free(ctx, d_cnt);
   tc_free(ctx, d_fb);
-  return TC_OK;
+  return st;
 }
 
 int tci_radius_search_launch(tc_context* ctx, const tc_index* ix, const float q[3], float radius,
