@@ -126,7 +126,9 @@ int tc_statistical_outlier_removal(tc_context* ctx, const tc_cloud* cloud, uint3
  * into float4 (x,y,z,original index) sorted by cell; up to three resolutions when the density is
  * strongly skewed (LiDAR).  cell_size <= 0 selects the cell edge automatically from `k_hint`
  * (the k the index will mostly be queried with; 1 for ICP correspondence search); an explicit
- * cell_size builds exactly one level.  Coordinates must be finite (TC_INVALID_DATA otherwise). */
+ * cell_size builds exactly one level.  Coordinates must be finite: NaN / Inf anywhere in a cloud
+ * (index build, kNN queries, ICP source, filters) is TC_INVALID_DATA - a documented deviation from
+ * the reference, whose KdTree::new accepts them and treats NaN as "Equal" in comparisons. */
 int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
                    tc_index** out);
 void tc_index_free(tc_index* index);

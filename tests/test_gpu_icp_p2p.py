@@ -61,3 +61,26 @@ def test_parity_two_scans_not_converged_and_max_distance(orc):
     got = tc.icp_detailed(src, tgt, tc.IDENTITY, 8, 0.05, 1e-7)
     ref = orc.icp_point_to_point(src, tgt, max_iters=8, conv=1e-7, max_dist=0.05)
     _compare(got, ref)
+
+
+def test_not_converged_mse_counts_accepted_pairs_only(orc):
+    """registration.rs:342-361: when the loop ends without converging the reported mse is over the
+    ACCEPTED correspondences of the last iteration; pairs the max-distance test rejected keep
+    seeding the next search but must not enter that mean."""
+    src, tgt, _, T = synth.scan_pair(40_000, half_extent=10.0)
+    # a third of the source is pushed 0.3 m off the surface: rejected at max distance 0.08
+    src = src.copy()
+    src[::3, 2] += np.float32(0.3)
+    got = tc.icp_detailed(src, tgt, tc.IDENTITY, 5, 0.08, -1.0)
+    ref = orc.icp_point_to_point(src, tgt, max_iters=5, conv=-1.0, max_dist=0.08, validate_conv=False)
+    assert not got.converged and got.iterations == 5
+    assert len(got.correspondences) < 0.8 * len(src)          # pairs really were rejected
+    _compare(got, ref)
+
+
+def test_gicp_negative_max_distance_rejects_every_pair():
+    """GicpConfig.max_correspondence_distance is a plain f32: negative means no pair passes
+    `dist > max` (gicp.rs:207-213) -> insufficient correspondences."""
+    src, tgt, _, _ = synth.scan_pair(3000, half_extent=3.0)
+    with pytest.raises(tc.AlgorithmError):
+        tc.gicp(src, tgt, tc.IDENTITY, tc.GicpConfig(max_correspondence_distance=-1.0))

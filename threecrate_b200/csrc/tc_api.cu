@@ -802,6 +802,10 @@ extern "C" int tc_gicp(tc_context* ctx, const float* src_aos, uint64_t ns, const
                        "dimension = " + buf + "); GICP requires 3-D structure");
     }
   }
+  // GicpConfig.max_correspondence_distance is a plain f32 (no Option): a negative value makes
+  // `dist > max` true for every pair, i.e. the reference finds no correspondences (gicp.rs:207-213)
+  if (st == TC_OK && max_correspondence_distance < 0.0f)
+    st = tc_fail(ctx, TC_ALGORITHM, "GICP: insufficient correspondences (need >= 6)");
   if (st == TC_OK) st = tci_gicp_covariances(ctx, src, min_k, &d_scov);
   if (st == TC_OK) st = tci_gicp_covariances(ctx, tgt, min_k, &d_tcov);
   if (st == TC_OK) st = tc_index_build(ctx, tgt, 1, 0.0f, &ix);

@@ -141,6 +141,12 @@ bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
   comm->epoch += epochs_needed;
   return true;
 }
+// Epochs are consumed one per executed exchange, so consecutive calls use consecutive epochs and
+// the two parity slots alternate across call boundaries as well: a rank that has started the next
+// call can only be one epoch ahead of a rank still reading the previous call's last slot.
+void tci_comm_commit_epochs(tc_comm* comm, unsigned long long used) {
+  if (comm) comm->epoch += used;
+}
 
 extern "C" void tc_comm_destroy(tc_comm* comm) {
   if (!comm) return;

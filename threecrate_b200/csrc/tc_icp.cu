@@ -20,6 +20,7 @@ int tci_comm_allreduce(tc_comm* comm, double* d_buf, uint64_t count);  // tc_com
 // peer exchange (tc_comm.cu): returns false when the communicator has no mapped peer buffers
 bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
                     unsigned long long* epoch_base, unsigned long long epochs_needed);
+void tci_comm_commit_epochs(tc_comm* comm, unsigned long long used);
 int g_tc_icp_solve_fused = 1;  // debug: 0 = separate solve launch
 extern "C" void tc_debug_set_icp_solve_fused(int on) { g_tc_icp_solve_fused = on; }
 extern int g_tc_icp_fuse;  // 1 (default): fused tail; 0: separate all-reduce + solve launches
@@ -59,6 +60,7 @@ struct PeerXchg {
   double* peer[8];     // peer[r] = rank r's buffer as mapped into THIS process (peer[rank] local)
   int world, rank;
   unsigned long long epoch_base;
+  unsigned long long spin_limit;  // polls (64 ns apart) before a missing peer fails the call
 };
 constexpr int kXSlot = 32;
 
@@ -424,7 +426,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
           unsigned long long spins = 0;
           while (*f != (double)epoch) {
             __nanosleep(64);
-            if (++spins > (1ull << 24)) {  // ~1 s: a peer died; fail instead of hanging the GPU
+            if (++spins > px.spin_limit) {  // a peer died: fail instead of hanging the GPU
               ok = false;
               break;
             }
@@ -814,6 +816,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   if (st == TC_OK) st = tc_alloc(ctx, &d_final, 2);
   IcpState h_state{};
   double h_final[2] = {0.0, 0.0};
+  bool fuse_used = false;
   if (st == TC_OK) {
     if (mode == kPlane) {
       k_pad_normals<<<std::max(1, std::min((int)((nt + kIcpBlock - 1) / kIcpBlock),
@@ -831,8 +834,17 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
     px.world = 1;
     int fuse = 0;
     if (comm && g_tc_icp_fuse &&
-        tci_comm_peers(comm, px.peer, &px.world, &px.rank, &px.epoch_base, max_iters + 1))
+        tci_comm_peers(comm, px.peer, &px.world, &px.rank, &px.epoch_base, 0))
       fuse = 1;
+    {
+      // how long a rank waits for its peers' sums before giving up (TC_GPU instead of a hang):
+      // generous by default - ranks legitimately arrive seconds apart (first-call set-up, an
+      // uneven index build); TC_PEER_TIMEOUT_S overrides
+      double secs = 30.0;
+      if (const char* e = std::getenv("TC_PEER_TIMEOUT_S")) secs = std::max(0.1, atof(e));
+      px.spin_limit = (unsigned long long)(secs / 100e-9);  // ~100 ns per poll incl. the sleep
+    }
+    fuse_used = fuse != 0;
     const int solve_here = (!comm || fuse) && g_tc_icp_solve_fused ? 1 : 0;
     for (uint32_t it = 0; it < max_iters && st == TC_OK; ++it) {
       if (mode == kGicp)
@@ -878,6 +890,12 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
       if (e != cudaSuccess)
         st = tc_fail(ctx, TC_GPU, std::string("ICP failed: ") + cudaGetErrorString(e));
     }
+  }
+  if (fuse_used) {
+    // one epoch per executed exchange; an iteration that stopped in the solve (too few pairs,
+    // singular system) had exchanged already.  Every rank sees the same sums, hence the same count.
+    const bool stopped_in_solve = h_state.status == 2 || h_state.status == 3;
+    tci_comm_commit_epochs(comm, (unsigned long long)h_state.iterations + (stopped_in_solve ? 1 : 0));
   }
   tc_free(ctx, d_src);
   tc_free(ctx, d_prev);
