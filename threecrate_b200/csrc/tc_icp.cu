@@ -22,6 +22,8 @@ bool tci_comm_peers(tc_comm* comm, double** peers8, int* world, int* rank,
                     unsigned long long* epoch_base, unsigned long long epochs_needed);
 void tci_comm_commit_epochs(tc_comm* comm, unsigned long long used);
 int g_tc_icp_solve_fused = 1;  // debug: 0 = separate solve launch
+int g_tc_icp_keep = 1;         // debug: 0 = search every point every iteration (A/B of the skip)
+extern "C" void tc_debug_set_icp_keep(int on) { g_tc_icp_keep = on; }
 extern "C" void tc_debug_set_icp_solve_fused(int on) { g_tc_icp_solve_fused = on; }
 extern int g_tc_icp_fuse;  // 1 (default): fused tail; 0: separate all-reduce + solve launches
 
@@ -127,7 +129,8 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
                  const float4* __restrict__ src_cov, const float4* __restrict__ src, uint32_t ns,
                  float max_dist, IcpState* __restrict__ st, double* __restrict__ partials,
                  double* __restrict__ sums, uint32_t* __restrict__ match_out,
-                 uint32_t* __restrict__ prev, int fuse, PeerXchg px, int solve_here, float conv) {
+                 uint32_t* __restrict__ prev, float4* __restrict__ cache, int fuse, PeerXchg px,
+                 int solve_here, float conv) {
   if (st->done) return;
   float T[7];
 #pragma unroll
@@ -176,6 +179,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
       Best1 best;
       int level, start = -1;
       const uint32_t seed = prev ? prev[i] : 0xFFFFFFFFu;
+      bool keep = false;  // last iteration's match is provably still the nearest: no search
       if (seed != 0xFFFFFFFFu) {
         start = (int)(seed >> 30);
         best.pos = seed & 0x3FFFFFFFu;
@@ -183,8 +187,23 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         const float d2 = dist2_exact(c.x, c.y, c.z, s.x, s.y, s.z);
         best.key = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
         best.seeded = true;
+        // cache = (query position at the last full search, lower bound `a` on the distance from
+        // THAT position to every target point other than the match).  By the triangle inequality
+        // every other point is now at least a - |s - q_full| away; if the match is strictly closer
+        // than that (with slack for f32 rounding of the coordinates, 3e-7 |s|, and of the
+        // distances, 2e-5 relative) the reference's 1-NN cannot be anything else, ties included.
+        if (cache) {
+          const float4 cf = cache[i];  // (all NaN before the point's first search)
+          const float mx = s.x - cf.x, my = s.y - cf.y, mz = s.z - cf.z;
+          const float moved = sqrtf(mx * mx + my * my + mz * mz);
+          const float dist = sqrtf(d2);
+          const float lhs = (dist + moved) * 1.00002f +
+                            3e-7f * (fabsf(s.x) + fabsf(s.y) + fabsf(s.z));
+          keep = cf.w > 0.0f && lhs < cf.w * 0.99998f;
+          level = start;
+        }
       }
-      {
+      if (!keep) {
         // Seeded (level << 30 | position of last iteration's match): a box query around the seed
         // distance - one or two rows of one or two cells once the pose has settled.  Without a
         // seed (first iteration), or when the pose jumped and the old match is cells away (second
@@ -195,6 +214,9 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         const float4* __restrict__ pts = ls.pts[level];
         const uint32_t* __restrict__ cs = ls.cs[level];
         auto scan = [&](uint32_t lo, uint32_t hi) { best.scan(pts, lo, hi, s.x, s.y, s.z, 0); };
+        float covered = -1.0f;  // radius of the ball around s whose cells were all scanned
+        bool probed = false;
+        int px0 = 0, px1 = 0, py0 = 0, py1 = 0, pz0 = 0, pz1 = 0;  // cells the probe scanned
         if (!best.seeded || best.kth() > g.cell * g.cell * 0.5f) {
           best.init();
           float ux, uy, uz;
@@ -211,9 +233,37 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
             const uint32_t row = cell_id(g, 0, y, z);
             scan(__ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]));
           }
+          probed = !best.seeded;  // (a far seed may lie outside the probed rows: not "all scanned")
+          px0 = x0;
+          px1 = x1;
+          py0 = min(cy, y2);
+          py1 = max(cy, y2);
+          pz0 = min(cz, z2);
+          pz1 = max(cz, z2);
         }
-        if (best.full()) box_visit(g, cs, s.x, s.y, s.z, best.kth(), scan);
-        else level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
+        if (best.full()) {
+          float r2 = best.kth();
+          // Seeded: the ball is taken 1.25x wider than the distance in hand.  What that costs in
+          // extra cells buys the bound (distance to every OTHER point) that lets the following
+          // iterations keep the match without any search.  Unseeded (first iteration): no margin,
+          // and the 2x2 probed rows usually contain the whole ball already - nothing left to visit.
+          bool inside = false;
+          if (best.seeded && cache) {
+            r2 *= 1.5625f;
+          } else if (probed) {
+            const BoxCells bc = box_cells(g, s.x, s.y, s.z, r2);
+            inside = bc.xa >= px0 && bc.xb <= px1 && bc.ya >= py0 && bc.yb <= py1 && bc.za >= pz0 &&
+                     bc.zb <= pz1;
+          }
+          if (!inside) box_visit(g, cs, s.x, s.y, s.z, r2, scan);
+          covered = sqrtf(r2);
+        } else {
+          level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
+        }
+        if (cache)
+          cache[i] = make_float4(s.x, s.y, s.z,
+                                 (best.full() && covered > 0.0f) ? fminf(sqrtf(best.second), covered)
+                                                                 : -1.0f);
       }
       valid = best.full();
       if (prev) prev[i] = valid ? (((uint32_t)level << 30) | best.pos) : 0xFFFFFFFFu;
@@ -798,6 +848,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   float4* d_nrm = nullptr;
   uint32_t* d_prev = nullptr;
   uint32_t* d_match_own = nullptr;  // kPoint + max distance: acceptance record for the final mse
+  float4* d_cache = nullptr;        // per source point: position + bound of its last full search
   IcpState* d_state = nullptr;
   double *d_partials = nullptr, *d_sums = nullptr, *d_final = nullptr;
   int st = TC_OK;
@@ -806,6 +857,8 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   if (st == TC_OK && nt < (1u << 30) && ns > 0) {
     st = tc_alloc(ctx, &d_prev, ns);
     if (st == TC_OK) cudaMemsetAsync(d_prev, 0xFF, (size_t)ns * sizeof(uint32_t), ctx->stream);
+    if (st == TC_OK && g_tc_icp_keep) st = tc_alloc(ctx, &d_cache, ns);  // bound = NaN: unknown
+    if (st == TC_OK && d_cache) cudaMemsetAsync(d_cache, 0xFF, (size_t)ns * sizeof(float4), ctx->stream);
   }
   if (st == TC_OK && mode == kPoint && max_corr_dist >= 0.0f && !d_match_out && ns > 0) {
     st = tc_alloc(ctx, &d_match_own, ns);
@@ -850,15 +903,15 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
       if (mode == kGicp)
         k_icp_correspond<kGicp><<<grid, kIcpBlock, 0, ctx->stream>>>(
             ls, d_tgt_cov, d_src_cov, d_src, ns, max_corr_dist, d_state, d_partials, d_sums,
-            d_match_out, d_prev, fuse, px, solve_here, conv_threshold);
+            d_match_out, d_prev, d_cache, fuse, px, solve_here, conv_threshold);
       else if (mode == kPlane)
         k_icp_correspond<kPlane><<<grid, kIcpBlock, 0, ctx->stream>>>(
             ls, d_nrm, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out, d_prev,
-            fuse, px, solve_here, conv_threshold);
+            d_cache, fuse, px, solve_here, conv_threshold);
       else
         k_icp_correspond<kPoint><<<grid, kIcpBlock, 0, ctx->stream>>>(
             ls, nullptr, nullptr, d_src, ns, max_corr_dist, d_state, d_partials, d_sums, d_match_out,
-            d_prev, fuse, px, solve_here, conv_threshold);
+            d_prev, d_cache, fuse, px, solve_here, conv_threshold);
       ctx->launches++;
       if (solve_here) continue;
       st = tci_comm_allreduce(comm, d_sums, n_sums);
@@ -899,6 +952,7 @@ int icp_device_impl(int mode, tc_context* ctx, tc_comm* comm, const tc_cloud* sr
   }
   tc_free(ctx, d_src);
   tc_free(ctx, d_prev);
+  tc_free(ctx, d_cache);
   tc_free(ctx, d_match_own);
   tc_free(ctx, d_nrm);
   tc_free(ctx, d_state);

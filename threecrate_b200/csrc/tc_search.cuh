@@ -238,6 +238,12 @@ struct Best1 {
   uint64_t key;
   uint32_t pos;
   bool seeded = false;
+  // smallest d2 among the scanned candidates OTHER than the current best (a candidate bit-equal
+  // to the best in d2 and index - the seed met again - does not count; an exact duplicate with
+  // another index does).  With the radius of the fully searched ball it bounds the distance to
+  // every other point from below, which lets the next ICP iteration keep the match without a
+  // search while the query has moved less than the gap (tc_icp.cu).
+  float second = INFINITY;
   __device__ __forceinline__ void init() {
     if (seeded) return;
     key = kEmpty;
@@ -260,9 +266,14 @@ struct Best1 {
         const float d2 = dist2_exact(c[t].x, c[t].y, c[t].z, qx, qy, qz);
         const uint64_t k2 =
             ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c[t].w);
-        if (k2 < key) {
-          key = k2;
-          pos = min(base + t, last);
+        if (base + t <= last) {  // (clamped repeats of the last candidate are not candidates)
+          if (k2 < key) {
+            second = fminf(second, kth());  // the displaced best (NaN when there was none)
+            key = k2;
+            pos = base + t;
+          } else if (k2 != key) {
+            second = fminf(second, d2);
+          }
         }
       }
     }
@@ -475,6 +486,24 @@ __device__ __forceinline__ void grid_visit(const GridParams& g, const uint32_t* 
 // square root and of q -+ r).  Used where a distance bound is already known: ICP correspondences
 // seeded with the previous iteration's match (or a probe), radius queries, the radius outlier
 // count.  The box is fixed on entry; `f` may tighten its own acceptance test while iterating.
+struct BoxCells {
+  int xa, xb, ya, yb, za, zb;
+};
+// cells that can hold a point within squared distance r2 (finite) of the query
+__device__ __forceinline__ BoxCells box_cells(const GridParams& g, float qx, float qy, float qz,
+                                              float r2) {
+  const float r = xsqrt(r2) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell) +
+                  1e-30f;
+  float u;
+  BoxCells b;
+  b.xa = cell_coord(qx - r, g.ox, g.inv, g.nx, u);
+  b.xb = cell_coord(qx + r, g.ox, g.inv, g.nx, u);
+  b.ya = cell_coord(qy - r, g.oy, g.inv, g.ny, u);
+  b.yb = cell_coord(qy + r, g.oy, g.inv, g.ny, u);
+  b.za = cell_coord(qz - r, g.oz, g.inv, g.nz, u);
+  b.zb = cell_coord(qz + r, g.oz, g.inv, g.nz, u);
+  return b;
+}
 template <class F>
 __device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* __restrict__ cell_start,
                                           float qx, float qy, float qz, float r2, F&& f) {
@@ -486,12 +515,8 @@ __device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* _
       }
     return;
   }
-  const float r = xsqrt(r2) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell) +
-                  1e-30f;
-  float u;
-  const int xa = cell_coord(qx - r, g.ox, g.inv, g.nx, u), xb = cell_coord(qx + r, g.ox, g.inv, g.nx, u);
-  const int ya = cell_coord(qy - r, g.oy, g.inv, g.ny, u), yb = cell_coord(qy + r, g.oy, g.inv, g.ny, u);
-  const int za = cell_coord(qz - r, g.oz, g.inv, g.nz, u), zb = cell_coord(qz + r, g.oz, g.inv, g.nz, u);
+  const BoxCells bc = box_cells(g, qx, qy, qz, r2);
+  const int xa = bc.xa, xb = bc.xb, ya = bc.ya, yb = bc.yb, za = bc.za, zb = bc.zb;
   for (int z = za; z <= zb; ++z)
     for (int y = ya; y <= yb; ++y) {
       const uint32_t row = cell_id(g, 0, y, z);

@@ -104,11 +104,13 @@ if "c3" in what:
     base_index = tc.GridIndex(tcloud, k_hint=1)
     auto = base_index.info()["cell_size"]
     ref = None
+    lib.tc_debug_set_icp_keep.argtypes = [C.c_int]
     for sc in scales:
         index = base_index if sc == 1.0 else tc.GridIndex(tcloud, k_hint=1, cell_size=auto * sc)
         info = index.info()
         for f in flags:
-            setflags(f)
+            setflags(f & 0xFFFF)
+            lib.tc_debug_set_icp_keep(0 if (f >> 16) & 1 else 1)   # flag bit 16: search every time
             res = []
             ms = timed(lambda: res.append(tc.icp_point_to_plane_device(
                 scloud, index, d_nrm, tc.IDENTITY, 30, None, -1.0)), 3)
