@@ -321,8 +321,10 @@ k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t
   }
 }
 
+// (72 registers for the 16-wide list: 7 blocks per SM, +6 % on the 10M cloud; the 32-wide list
+//  keeps ptxas' own choice of 96 - a forced 5 blocks/SM spills and loses)
 template <int L, bool X>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, L == 16 ? 7 : 0)
 k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, uint32_t own_end,
            uint32_t k, int orient, float vpx, float vpy, float vpz, float* __restrict__ out,
            uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,

@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["c2", "c4", "c3", "knn", "gicp", "filters"])
 ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--k", type=int, default=30)
+ap.add_argument("--iters", type=int, default=5)
 a = ap.parse_args()
 ctx = tc.default_context()
 
@@ -39,8 +41,8 @@ elif a.what == "c4":
     cloud = tc.DeviceCloud(pts, ctx)
     d_out = ctx.alloc(n * 24)
     for _ in range(a.reps):
-        index = tc.GridIndex(cloud, k_hint=30)
-        index.estimate_normals_device(d_out, 30)
+        index = tc.GridIndex(cloud, k_hint=a.k)
+        index.estimate_normals_device(d_out, a.k)
         ctx.synchronize()
         print(index.info())
         index.free()
@@ -52,7 +54,7 @@ elif a.what == "c3":
     ctx.to_device(d_nrm, nrm)
     for _ in range(a.reps):
         index = tc.GridIndex(tcloud, k_hint=1)
-        r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, 5, None, -1.0)
+        r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, a.iters, None, -1.0)
         print(index.info(), r.translation)
         index.free()
 elif a.what == "gicp":
