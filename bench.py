@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the C2/C3/C4/C5 extra workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-c5", action="store_true", help="skip the 100M-point ICP extra")
+    ap.add_argument("--only", default="", help="comma list of extras to run (c4,c3,c2,c5,next_rows)")
     ap.add_argument("--points", type=int, default=N_HEAD, help="headline cloud size")
     ap.add_argument("--c3-points", type=int, default=1_000_000)
     ap.add_argument("--c5-target", type=int, default=100_000_000)
@@ -468,6 +469,8 @@ def main():
                          ("c2", lambda: bench_c2(E) if world == 1 else {}),
                          ("c5", lambda: bench_c5(E) if not args.no_c5 else {}),
                          ("next_rows", lambda: bench_next_rows(E) if rank == 0 and world == 1 else {})):
+            if args.only and name not in args.only.split(","):
+                continue
             try:
                 extra.update(fn())
             except Exception as e:

@@ -36,12 +36,15 @@ def _hdr_mtime():
     return max(_mtime(h if os.path.isabs(h) else os.path.join(CSRC, h)) for h in HEADERS)
 
 
+EXTRA_DEFS: list = []  # e.g. ["-DTC_QCLOCK"] (tools/qclock.py)
+
+
 def _compile(src: str, force: bool, verbose: bool):
     s = os.path.join(CSRC, src)
     o = os.path.join(OBJ, src.replace(".cu", ".o"))
     if not force and _mtime(o) > max(_mtime(s), _hdr_mtime()):
         return o, ""
-    cmd = [NVCC, *ARCH, *CFLAGS, "-c", s, "-o", o]
+    cmd = [NVCC, *ARCH, *CFLAGS, *EXTRA_DEFS, "-c", s, "-o", o]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -90,4 +93,6 @@ def build_host_mirror_test(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--qclock" in sys.argv:  # per-query cycle counters compiled into the search kernels
+        EXTRA_DEFS.append("-DTC_QCLOCK")
+    print(build(force="--force" in sys.argv or "--qclock" in sys.argv, verbose="--verbose" in sys.argv))

@@ -18,6 +18,7 @@ extern "C" const char* tc_version(void) { return "threecrate_cuda 0.1.0 (sm_100a
 // ------------------------------------------------------------------------------------ context
 extern "C" void tc_debug_set_search_flags(int flags);
 extern "C" void tc_debug_set_fine_cap(int cells_per_point);
+extern "C" void tc_debug_set_icp_keep(int on);
 
 extern "C" int tc_context_create(int device, tc_context** out) {
   if (!out) return TC_INVALID_DATA;
@@ -56,6 +57,7 @@ extern "C" int tc_context_create(int device, tc_context** out) {
   // debug overrides for A/B runs of unmodified callers (tools/, bench.py)
   if (const char* e = std::getenv("TC_SEARCH_FLAGS")) tc_debug_set_search_flags(atoi(e));
   if (const char* e = std::getenv("TC_FINE_CAP")) tc_debug_set_fine_cap(atoi(e));
+  if (const char* e = std::getenv("TC_ICP_KEEP")) tc_debug_set_icp_keep(atoi(e));
   *out = ctx;
   return TC_OK;
 }

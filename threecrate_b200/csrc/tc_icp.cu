@@ -241,14 +241,26 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
           pz0 = min(cz, z2);
           pz1 = max(cz, z2);
         }
-        if (best.full()) {
+        // Nothing in hand (the probe found no point), or the match is more than four cells away
+        // (first iterations of a badly aligned pair): the ring search grows cell by cell from the
+        // query, nearest rows first, and prunes rows / cells that cannot beat the best distance -
+        // a fixed cube of that half-width would distance-test every point of the surface patch
+        // inside it.  One call site for both cases (the search code is large).
+        const bool far = !best.full() || best.kth() > 16.0f * g.cell * g.cell;
+        if (far) {
+          const bool have = best.full();
+          if (have) best.seeded = true;  // keep the candidate in hand as the pruning bound
+          level_search(ls, s.x, s.y, s.z, 1u, best, level, have ? level : -1);
+          if (have && best.full()) covered = sqrtf(best.kth());
+        } else {
           float r2 = best.kth();
-          // Seeded: the ball is taken 1.25x wider than the distance in hand.  What that costs in
-          // extra cells buys the bound (distance to every OTHER point) that lets the following
-          // iterations keep the match without any search.  Unseeded (first iteration): no margin,
-          // and the 2x2 probed rows usually contain the whole ball already - nothing left to visit.
+          // Seeded and within one cell of the match: the ball is taken 1.25x wider than the
+          // distance in hand.  What that costs in extra cells buys the bound (distance to every
+          // OTHER point) that lets the following iterations keep the match without any search.
+          // Unseeded (first iteration): no margin, and the 2x2 probed rows usually contain the
+          // whole ball already - nothing left to visit.
           bool inside = false;
-          if (best.seeded && cache) {
+          if (best.seeded && cache && r2 < g.cell * g.cell) {
             r2 *= 1.5625f;
           } else if (probed) {
             const BoxCells bc = box_cells(g, s.x, s.y, s.z, r2);
@@ -257,8 +269,6 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
           }
           if (!inside) box_visit(g, cs, s.x, s.y, s.z, r2, scan);
           covered = sqrtf(r2);
-        } else {
-          level_search(ls, s.x, s.y, s.z, 1u, best, level, -1);
         }
         if (cache)
           cache[i] = make_float4(s.x, s.y, s.z,

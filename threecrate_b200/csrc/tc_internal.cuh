@@ -36,7 +36,9 @@ struct tc_context {
   // small grow-only device workspaces reused across calls (index-build histograms, fallback
   // lists): every allocation call costs the host 1-2 us and the LiDAR-frame path is host-bound
   static constexpr int kWsSlots = 3;
-  static constexpr uint64_t kWsMaxBytes = 64ull << 20;  // larger requests are not cached
+  static constexpr uint64_t kWsMaxBytes = 1ull << 30;  // larger requests are not cached (a
+                                   // cudaMallocAsync of hundreds of MB right after a stream
+                                   // synchronisation costs 0.5 - 50 ms of host time)
   void* ws[kWsSlots] = {nullptr, nullptr, nullptr};
   uint64_t ws_bytes[kWsSlots] = {0, 0, 0};
   bool ws_zero[kWsSlots] = {false, false, false};  // cached buffer known to be all zero

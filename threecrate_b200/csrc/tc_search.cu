@@ -14,6 +14,21 @@
 #include "tc_search.cuh"
 #include "tc_normal.cuh"
 
+// Per-query cycle counters for tools/qclock.py exist only in a -DTC_QCLOCK build
+// (python -m threecrate_b200.build --qclock): the release kernels carry neither the extra
+// parameter nor the clock reads.
+#ifdef TC_QCLOCK
+#define TC_DBG_PARAM , uint32_t* __restrict__ dbg
+#define TC_DBG_PARAM_DEF , uint32_t* dbg = nullptr
+#define TC_DBG_ARG(x) , x
+#define TC_DBG(...) __VA_ARGS__
+#else
+#define TC_DBG_PARAM
+#define TC_DBG_PARAM_DEF
+#define TC_DBG_ARG(x)
+#define TC_DBG(...)
+#endif
+
 namespace {
 
 constexpr int kBlock = 128;
@@ -31,7 +46,7 @@ template <int L, bool X>
 __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, float qy, float qz,
                                                uint32_t need, uint32_t (*s_a)[kBlock],
                                                uint32_t (*s_b)[kBlock], int& level,
-                                               uint32_t* dbg = nullptr, int* R_out = nullptr) {
+                                               int* R_out = nullptr TC_DBG_PARAM_DEF) {
   constexpr int T = SelF<L, X>::kSlots;  // rows of s_a / s_b
   SelF<L, X> sel;
   sel.pad = T - (int)need;
@@ -41,10 +56,10 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
   const float4* __restrict__ pts = ls.pts[level];
   const uint32_t* __restrict__ cell_start = ls.cs[level];
   const float tau = sel.kth();  // +inf when fewer than `need` points exist: everything is kept
-  if (dbg) {
+  TC_DBG(if (dbg) {
     dbg[4] = (uint32_t)clock64();
     dbg[6] = (uint32_t)R;
-  }
+  })
   uint32_t n = 0;
   grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t j = lo; j < hi; ++j) {
@@ -76,7 +91,7 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
     }
     if (rank < (int)need) s_b[rank][threadIdx.x] = j;
   }
-  if (dbg) dbg[5] = (uint32_t)clock64();
+  TC_DBG(if (dbg) dbg[5] = (uint32_t)clock64();)
   if (n > need) n = need;
   return (int)n;
 }
@@ -301,23 +316,23 @@ __global__ void __launch_bounds__(kBlock)
 k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t q_end,
           uint32_t own_begin, uint32_t own_end, uint32_t k, int orient, float vpx, float vpy,
           float vpz, float* __restrict__ out, const uint32_t* __restrict__ list,
-          const uint32_t* __restrict__ list_count, uint32_t* __restrict__ dbg) {
+          const uint32_t* __restrict__ list_count TC_DBG_PARAM) {
   const uint32_t total = list ? *list_count : (q_end - q_begin);
   for (uint32_t t = blockIdx.x * kBlock + threadIdx.x; t < total; t += gridDim.x * kBlock) {
     const uint32_t qi = list ? list[t] : q_begin + t;
     const float4 q = __ldg(&ls.pts[0][qi]);
     if (!list && own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) continue;
     const uint32_t qid = __float_as_uint(q.w);
-    const long long t0 = dbg ? clock64() : 0;
+    TC_DBG(const long long t0 = dbg ? clock64() : 0;)
     TopK<K> tk;
     int level;
     const int R = level_search(ls, q.x, q.y, q.z, k + 1, tk, level);
     if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
     normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
-    if (dbg) {  // per-query cycles and final block radius (tools/qclock.py)
+    TC_DBG(if (dbg) {  // per-query cycles and final block radius (tools/qclock.py)
       dbg[8 * (size_t)qid] = (uint32_t)(clock64() - t0);
       dbg[8 * (size_t)qid + 1] = (uint32_t)R | ((uint32_t)level << 16);
-    }
+    })
   }
 }
 
@@ -327,14 +342,14 @@ template <int L, bool X>
 __global__ void __launch_bounds__(kBlock, L == 16 ? 7 : 0)
 k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, uint32_t own_end,
            uint32_t k, int orient, float vpx, float vpy, float vpz, float* __restrict__ out,
-           uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
-           uint32_t* __restrict__ dbg) {
+           uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count TC_DBG_PARAM) {
   __shared__ uint32_t s_a[L + (X ? 1 : 0)][kBlock], s_b[L + (X ? 1 : 0)][kBlock];
   const uint32_t qi = q_begin + blockIdx.x * kBlock + threadIdx.x;
   if (qi >= q_end) return;
   const float4 q = __ldg(&ls.pts[0][qi]);
   if (own_end != 0xFFFFFFFFu && !owns_query(ls, q, own_begin, own_end)) return;
   const uint32_t qid = __float_as_uint(q.w);
+#ifdef TC_QCLOCK
   const long long t0 = dbg ? clock64() : 0;
   if (dbg) {  // 8 words per query (tools/qclock.py): cycles, n|level, sorted position, start ns,
               // clock after pass 1, clock after pass 2 + rank, final block radius, start clock
@@ -345,8 +360,9 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
     dbg[3] = (uint32_t)ns;
     dbg[7] = (uint32_t)t0;
   }
+#endif
   int level, R = 0;
-  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, dbg, &R);
+  const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, &R TC_DBG_ARG(dbg));
   if (n < 0) {
     fb_list[atomicAdd(fb_count, 1u)] = qi;
     return;
@@ -354,10 +370,10 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
   if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
                out, (ls.g[0].flags & 128) != 0);
-  if (dbg) {
+  TC_DBG(if (dbg) {
     dbg[0] = (uint32_t)(clock64() - t0);
     dbg[1] = (uint32_t)n | ((uint32_t)level << 16);
-  }
+  })
 }
 
 // ------------------------------------------------------------------------------ radius mode
@@ -634,9 +650,17 @@ inline int pick_size(uint32_t need) {
 // bit 5 (32): staged-tile kernels (tc_tile.cu); bit 6 (64): TMA bulk staging (else LDG/STS);
 // bit 7 (128): Newton eigen solver with Jacobi fallback
 int g_tc_search_flags = 159;  // per-lane kernels + Newton; the staged-tile variant measured 13-17 % slower
+#ifdef TC_QCLOCK
 static uint32_t* g_tc_dbg = nullptr;  // optional per-query {cycles, R or n} buffer (8 u32 / point)
+#endif
 extern "C" void tc_debug_set_search_flags(int flags) { g_tc_search_flags = flags; }
-extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) { g_tc_dbg = (uint32_t*)d_buf; }
+extern "C" void tc_debug_set_query_clock_buffer(void* d_buf) {
+#ifdef TC_QCLOCK
+  g_tc_dbg = (uint32_t*)d_buf;
+#else
+  (void)d_buf;  // release build: no clock plumbing in the kernels (build with --qclock)
+#endif
+}
 
 #define TC_DISPATCH_K(SZ, CALL)                     \
   switch (SZ) {                                     \
@@ -782,8 +806,8 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   if (!two_pass) {
     TC_DISPATCH_K(sz, (k_normals<KK><<<grid, kBlock, 0, ctx->stream>>>(
                           ls, ix->cloud->d_xyz, (uint32_t)q_begin, (uint32_t)q_end, own_begin,
-                          own_end, k, orient, vp[0], vp[1], vp[2], d_out_aos, nullptr, nullptr,
-                          g_tc_dbg)));
+                          own_end, k, orient, vp[0], vp[1], vp[2], d_out_aos, nullptr,
+                          nullptr TC_DBG_ARG(g_tc_dbg))));
     TC_LAUNCHED(ctx);
     return TC_OK;
   }
@@ -793,7 +817,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
 #define TC_NORMALS2(LL, XX)                                                                  \
   k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
       ls, (uint32_t)q_begin, (uint32_t)q_end, own_begin, own_end, k, orient, vp[0], vp[1],   \
-      vp[2], d_out_aos, d_fb + 1, d_fb, g_tc_dbg)
+      vp[2], d_out_aos, d_fb + 1, d_fb TC_DBG_ARG(g_tc_dbg))
   if (flags & 32) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
     uint32_t* d_stats = nullptr;
     ctx->stats_queries = nq;
@@ -817,7 +841,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
   TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
                         ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1], vp[2],
-                        d_out_aos, d_fb + 1, d_fb, nullptr)));
+                        d_out_aos, d_fb + 1, d_fb TC_DBG_ARG(nullptr))));
   TC_LAUNCHED(ctx);
   tc_ws_release(ctx, 2, d_fb);
   return TC_OK;
@@ -890,7 +914,7 @@ int tci_normals_radius_launch(tc_context* ctx, const tc_index* ix, float radius,
       const dim3 fgrid(std::min<uint32_t>((n_fb + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count * 4));
       TC_DISPATCH_K(sz, (k_normals<KK><<<fgrid, kBlock, 0, ctx->stream>>>(
                             ls, ix->cloud->d_xyz, 0u, 0u, 0u, 0xFFFFFFFFu, k, orient, vp[0], vp[1],
-                            vp[2], d_out_aos, d_fb + 1, d_fb, nullptr)));
+                            vp[2], d_out_aos, d_fb + 1, d_fb TC_DBG_ARG(nullptr))));
       ctx->launches++;
     } else {  // k + 1 beyond the register lists: global-memory heaps over the list, in chunks
       const uint32_t hchunk = std::min(n_fb, kBigChunk);
