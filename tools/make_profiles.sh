@@ -16,7 +16,7 @@ run() { # tag what kernel-regex skip points extra-args
 run r02_head c4 k_normals2 1 10000000 --n 10000000 --k 16 --reps 2
 run r02_c4   c4 k_normals2 1 10000000 --n 10000000 --k 30 --reps 2
 run r02_c2   c2 k_normals2 1 120000 --reps 2
-run r02_c3   c3 k_icp_correspond 12 1000000 --reps 3
+run r02_c3   c3 k_icp_correspond 50 1000000 --reps 2 --iters 30
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_head.csv python tools/profile_targets.py c4 --n 10000000 --k 16 --reps 2 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_c4.csv python tools/profile_targets.py c4 --n 10000000 --k 30 --reps 2 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_c2.csv python tools/profile_targets.py c2 --reps 3 > /dev/null 2>&1
