@@ -56,7 +56,8 @@ BYTES_ICP_PER_PT_ITER = 36.0     # 12 B read + 24 B gathered                (SUR
 BYTES_INDEX_PER_PT = 52.0
 BYTES_INDEX_PER_CELL = 24.0
 WORKLOAD = ("estimate_normals k=16 on a 10,000,000-point synthetic terrain cloud (index build + "
-            "fused normals kernel), queries sharded over the ranks on a replicated grid")
+            "fused normals kernel); at N > 1 every rank builds the index of its slab of cell planes "
+            "(+ halo) and computes the rows of the points in its slab")
 
 
 def _peaks():
@@ -346,25 +347,30 @@ def main():
     grid_info = info.info()
     info.free()
 
-    # ---- e2e: host buffers through the drop-in C-ABI call, copies inside the timed region.
-    # At N > 1 there is no sharded host-buffer entry point in the reference's API: every rank
-    # uploads the cloud, builds, computes ITS shard and reads the full row buffer back.
+    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region.
+    # N = 1: the drop-in tc_estimate_normals.  N > 1: tc_estimate_normals_distributed - every rank
+    # passes ITS contiguous chunk of the rows (1/N of the upload), the chunks are exchanged over
+    # NVLink peer memory, and every rank gets the normal rows of its chunk back (1/N of the
+    # download); window set-up (once per cloud size) is outside the timed region like the
+    # communicator's.
     lib = ctx.lib
     import ctypes as C
     h_page_in = np.array(pts, copy=True)          # ordinary pageable memory (a Rust Vec<Point3f>)
     h_page_out = np.empty((n, 6), np.float32)
+    dcomm = None
+    if world > 1:
+        dcomm = _make_comm(E, peers=False)
+        wh = [None] * world
+        dist.all_gather_object(wh, dcomm.window_handle(n))
+        dcomm.open_window(wh)
+        c_lo, c_hi = dcomm.chunk(n)
 
     def e2e_pass(src, dst):
         if world == 1:
             ctx.check(lib.tc_estimate_normals(ctx.h, C.c_void_p(src.ctypes.data), n, K_HEAD, -1.0, 1,
                                               None, C.c_void_p(dst.ctypes.data)))
             return
-        c = tc.DeviceCloud(src, ctx)
-        ix = tc.GridIndex(c, k_hint=K_HEAD, shard=shard)
-        ix.estimate_normals_device(d_out, K_HEAD)
-        ctx.to_host(dst, d_out)
-        ix.free()
-        c.free()
+        dcomm.estimate_normals(src[c_lo:c_hi], n, K_HEAD, out=dst[c_lo:c_hi])
 
     def time_e2e(src, dst, steps):
         for _ in range(2):
@@ -375,6 +381,7 @@ def main():
         for _ in range(steps):
             flush_l2()
             ctx.synchronize()
+            barrier()               # (the call is collective: start the ranks together)
             t0 = time.perf_counter()
             e2e_pass(src, dst)      # returns after the D2H copy completed (synchronous host API)
             ms.append(1e3 * (time.perf_counter() - t0))
@@ -385,6 +392,25 @@ def main():
     e2e_pg_value, e2e_pg_ms = time_e2e(h_page_in, h_page_out, max(3, args.steps // 4))
     clocks = sampler.stop()
     del h_page_in, h_page_out
+    dist_parity = None
+    if world > 1:
+        # the rows the distributed call returned vs the single-GPU call, bit for bit
+        h_out[c_lo:c_hi] = 0
+        e2e_pass(h_in, h_out)
+        ix1 = tc.GridIndex(cloud, k_hint=K_HEAD)
+        ix1.estimate_normals_device(d_out, K_HEAD)
+        ref_rows = np.empty((n, 6), np.float32)
+        ctx.to_host(ref_rows, d_out)
+        ix1.free()
+        bad = int(np.any(h_out[c_lo:c_hi].view(np.uint32) != ref_rows[c_lo:c_hi].view(np.uint32),
+                         axis=1).sum())
+        bad_all = int(E.max_over_ranks(float(bad)))
+        dist_parity = {"rows_differing_max_over_ranks": bad_all,
+                       "bitwise_equal_to_single_gpu": bad_all == 0}
+        if bad_all:
+            E.parity_failures.append(f"distributed normals: {bad_all} rows differ")
+        del ref_rows
+        dcomm.destroy()
 
     # ---- roofline of the dominant kernel (this rank's launch), live CUDA-event time
     kern_s = float(np.mean(ms_kernel)) * 1e-3
@@ -441,9 +467,12 @@ def main():
                    "cpu_affinity": (f"NVML-local CPUs of the rank's GPU ({len(E.affinity)} cores)"
                                     if E.affinity else "unchanged")},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 12 * world),
-                "d2h_bytes_per_step": int(n * 24 * world), "ms_per_step": e2e_ms,
-                "host_memory": "pinned"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
+                "d2h_bytes_per_step": int(n * 24), "ms_per_step": e2e_ms,
+                "host_memory": "pinned",
+                "call": ("tc_estimate_normals" if world == 1 else
+                         "tc_estimate_normals_distributed (each rank moves its 1/N chunk of the "
+                         "rows over PCIe; chunks and result rows cross NVLink peer windows)")},
         "e2e_pageable": {"value": e2e_pg_value, "unit": UNIT, "ms_per_step": e2e_pg_ms,
                          "host_memory": "pageable (what a Rust Vec<Point3f> is)"},
         "gpu_launches": int(launches),
@@ -455,7 +484,8 @@ def main():
 
     # ---- N > 1: the sharded rows tile the cloud exactly once and equal the single-GPU result
     if world > 1:
-        line["parity"] = {"normals_k16": parity_normals(E, cloud, out_t, lo, hi, K_HEAD)}
+        line["parity"] = {"normals_k16": parity_normals(E, cloud, out_t, lo, hi, K_HEAD),
+                          "normals_k16_distributed_e2e": dist_parity}
 
     # -------------------------------------------------------------------------- cpu_baseline
     if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline is an N=1 figure
@@ -676,13 +706,15 @@ def bench_c2(E):
     return {"c2_normals_k16_kitti_frame": out}
 
 
-def _make_comm(E):
+def _make_comm(E, peers=True):
     tc, ctx, dist = E.tc, E.ctx, E.dist
     if E.world == 1:
         return None
     ids = [tc.Comm.unique_id(ctx) if E.rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     comm = tc.Comm(ctx, ids[0], E.world, E.rank)
+    if not peers:
+        return comm
     handles = [None] * E.world          # NVLink peer buffers for the fused all-reduce
     dist.all_gather_object(handles, comm.peer_handle())
     comm.open_peers(handles)

@@ -290,6 +290,25 @@ int tc_comm_peer_open(tc_comm* comm, const void* all_handles /* n_ranks * TC_IPC
 /* Sum-all-reduce of `count` f64 on the context's stream (exposed for tests). */
 int tc_comm_allreduce_f64(tc_comm* comm, double* d_buf, uint64_t count);
 
+/* ---- distributed estimate_normals (normals.rs:238-268 over the ranks of a tc_comm) ---------
+ * Strong scaling of ONE cloud: its rows are split into n_ranks contiguous chunks
+ * (tc_dist_chunk: equal lengths, a multiple of 4 rows; the last ranks may hold fewer rows or
+ * none).  Rank r passes its chunk of the points (HOST) and receives the NormalPoint3f rows of the
+ * same range (HOST), bit-identical to the single-GPU result.  Per call a rank uploads only its
+ * chunk, pulls the other chunks out of the peers' windows over NVLink, builds the slab-sharded
+ * index (tc_index_build_sharded), and its normals kernel writes every row straight into the
+ * window of the rank that owns it; two stream-ordered peer barriers, no collective call.
+ * Set-up (once per cloud size): every rank calls tc_comm_window_handle, the host gathers the
+ * handles of all ranks (rank order) and passes the concatenation to tc_comm_window_open.
+ * kNN mode only (radius-mode normals: shard tc_estimate_normals_device by sorted range). */
+void tc_dist_chunk(uint64_t n_total, int n_ranks, int rank, uint64_t* lo, uint64_t* hi);
+int tc_comm_window_handle(tc_comm* comm, uint64_t n_total, void* handle_out /* TC_IPC_HANDLE_BYTES */);
+int tc_comm_window_open(tc_comm* comm, const void* all_handles /* n_ranks * TC_IPC_HANDLE_BYTES */);
+int tc_estimate_normals_distributed(tc_context* ctx, tc_comm* comm, const float* chunk_xyz_aos,
+                                    uint64_t n_total, uint32_t k, int consistent_orientation,
+                                    const float* viewpoint3 /* NULL = reference default */,
+                                    float* chunk_out_aos /* (hi - lo) x 6 */);
+
 /* ---- raw device memory helpers for hosts without their own CUDA bindings ------------------- */
 int tc_device_alloc(tc_context* ctx, uint64_t bytes, void** d_out);
 int tc_device_free(tc_context* ctx, void* d_ptr);

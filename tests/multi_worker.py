@@ -71,6 +71,19 @@ dist.all_reduce(cnt)
 assert int(cnt.min()) == 1 and int(cnt.max()) == 1, "shards must tile the cloud exactly once"
 ref = ix.estimate_normals(16)
 assert np.array_equal(mine[written], ref[written])
+# ---- distributed estimate_normals: chunks in, chunks out, rows routed over NVLink windows
+for cloud_pts, kk in ((synth.terrain(300_001, 18.0, seed=11, noise=0.002), 16), (pts, 10)):
+    nn = len(cloud_pts)
+    wh = [None] * world
+    dist.all_gather_object(wh, comm.window_handle(nn))
+    comm.open_window(wh)
+    lo, hi = comm.chunk(nn)
+    full_ix = tc.GridIndex(tc.DeviceCloud(cloud_pts, ctx), k_hint=kk)
+    ref = full_ix.estimate_normals(kk)
+    for _ in range(3):
+        got = comm.estimate_normals(cloud_pts[lo:hi], nn, kk)
+        assert np.array_equal(got.view(np.uint32), ref[lo:hi].view(np.uint32)), \
+            "distributed normals differ from the single-GPU rows"
 dist.barrier()
 if rank == 0:
     print("MULTI_OK")

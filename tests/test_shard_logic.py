@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import threecrate_b200 as tc
 from threecrate_b200 import sharding
 from fixtures import synth
 
@@ -66,3 +67,69 @@ def test_gloo_allreduce_of_normal_equations_world2():
         assert same, "ranks disagree"
         assert err < 1e-9
         assert nvalid == 4000
+
+
+def test_distributed_normals_chunks_tile_and_route():
+    """tc_dist_chunk (the row split of tc_estimate_normals_distributed): contiguous, equal length,
+    a multiple of 4 rows (16-byte aligned chunk boundaries in the 12-byte point array), and the
+    kernel's routing rule `owner = i // chunk` sends every row to the rank whose range holds it."""
+    for n in (0, 1, 5, 1023, 120000, 10_000_001):
+        for w in (1, 2, 3, 8):
+            r = [tc.dist_chunk(n, w, i) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            chunk = max(4, -(-n // w) + 3 & ~3)
+            assert chunk % 4 == 0 and all(b - a in (chunk, max(0, n - i * chunk), 0)
+                                          for i, (a, b) in enumerate(r))
+            for i in (0, n // 3, n - 1):
+                if 0 <= i < n:
+                    a, b = r[i // chunk]
+                    assert a <= i < b
+                    # the device form: __umulhi(i, 2^32 // chunk), corrected upwards once
+                    q = (i * ((1 << 32) // chunk)) >> 32
+                    q += (q + 1) * chunk <= i
+                    assert q == i // chunk
+
+
+def _chunk_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pts = synth.terrain(1001, 5.0, seed=9)
+        n = len(pts)
+        lo, hi = tc.dist_chunk(n, world, rank)
+        chunk = tc.dist_chunk(n, world, 0)[1]
+        # all-gather of the chunks rebuilds the cloud (what k_gather_chunks does over NVLink)
+        mine = np.zeros((chunk, 3), np.float32)
+        mine[: hi - lo] = pts[lo:hi]
+        parts = [torch.zeros(chunk, 3) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(mine))
+        full = torch.cat(parts)[:n].numpy()
+        # every rank computes the rows of "its" points (here: a split by y) and routes row i to
+        # rank i // chunk: the owners end up with exactly their range, each row once
+        order = np.argsort(full[:, 1], kind="stable")
+        own = order[rank * n // world:(rank + 1) * n // world]
+        sent = torch.zeros(world * chunk, dtype=torch.int32)
+        sent[torch.from_numpy(own)] = 1
+        dist.all_reduce(sent)
+        q.put((rank, bool(np.array_equal(full, pts)), int(sent[:n].min()), int(sent[:n].max()),
+               int(sent[lo:hi].sum()) == hi - lo))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_chunk_gather_and_row_routing_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30000 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_chunk_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rebuilt, lo_cnt, hi_cnt, mine_complete in res:
+        assert rebuilt and lo_cnt == 1 and hi_cnt == 1 and mine_complete

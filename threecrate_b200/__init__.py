@@ -28,6 +28,7 @@ from .api import (  # noqa: F401
     NormalEstimationConfig,
     ThreecrateError,
     default_context,
+    dist_chunk,
     estimate_normals,
     estimate_normals_radius,
     estimate_normals_with_config,

@@ -122,6 +122,12 @@ SYMBOLS = {
     "tc_comm_allreduce_f64": (C.c_int, [_vp, _vp, C.c_uint64]),
     "tc_comm_peer_handle": (C.c_int, [_vp, _vp]),
     "tc_comm_peer_open": (C.c_int, [_vp, _vp]),
+    "tc_dist_chunk": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                             C.POINTER(C.c_uint64)]),
+    "tc_comm_window_handle": (C.c_int, [_vp, C.c_uint64, _vp]),
+    "tc_comm_window_open": (C.c_int, [_vp, _vp]),
+    "tc_estimate_normals_distributed": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int,
+                                                  _vp, _vp]),
     "tc_device_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "tc_device_free": (C.c_int, [_vp, _vp]),
     "tc_copy_to_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),

@@ -668,6 +668,13 @@ def gicp(source, target, init=IDENTITY, config: Optional[GicpConfig] = None,
 # --------------------------------------------------------------------------------------------
 # multi-GPU (one process per GPU)
 # --------------------------------------------------------------------------------------------
+def dist_chunk(n_total: int, n_ranks: int, rank: int):
+    """tc_dist_chunk: the contiguous row range of rank `rank` (equal lengths, multiple of 4)."""
+    lo, hi = C.c_uint64(), C.c_uint64()
+    _lib.load().tc_dist_chunk(int(n_total), int(n_ranks), int(rank), C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
 class Comm:
     """NCCL communicator for the sharded ICP reduction (tc_comm).  The 128-byte unique id is
     produced on rank 0 and handed to the other ranks by the host (torch.distributed here)."""
@@ -699,6 +706,42 @@ class Comm:
         blob = b"".join(handles)
         assert len(blob) == self.n_ranks * _lib.TC_IPC_HANDLE_BYTES
         self.ctx.check(self.ctx.lib.tc_comm_peer_open(self.h, C.create_string_buffer(blob, len(blob))))
+
+    # ---- distributed normals (tc_estimate_normals_distributed) ------------------------------
+    def chunk(self, n_total: int):
+        """Rows [lo, hi) of an n_total-row cloud this rank passes in and gets back."""
+        return dist_chunk(n_total, self.n_ranks, self.rank)
+
+    def window_handle(self, n_total: int) -> bytes:
+        """Allocates this rank's NVLink window for clouds of n_total points and returns its IPC
+        handle (gather from all ranks, then `open_window`)."""
+        buf = C.create_string_buffer(_lib.TC_IPC_HANDLE_BYTES)
+        self.ctx.check(self.ctx.lib.tc_comm_window_handle(self.h, int(n_total), buf))
+        return buf.raw
+
+    def open_window(self, handles) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == self.n_ranks * _lib.TC_IPC_HANDLE_BYTES
+        self.ctx.check(self.ctx.lib.tc_comm_window_open(self.h, C.create_string_buffer(blob, len(blob))))
+
+    def estimate_normals(self, chunk_xyz: np.ndarray, n_total: int, k: int,
+                         consistent_orientation: bool = True, viewpoint=None,
+                         out: Optional[np.ndarray] = None) -> np.ndarray:
+        """estimate_normals of ONE cloud over all ranks: pass this rank's rows (`chunk(n_total)`)
+        and get the NormalPoint3f rows of the same range (bit-identical to the single-GPU
+        result).  Collective: every rank must call it."""
+        lo, hi = self.chunk(n_total)
+        pts = np.ascontiguousarray(chunk_xyz, np.float32).reshape(-1, 3)
+        if len(pts) != hi - lo:
+            raise InvalidData(f"rank {self.rank} passes rows [{lo}, {hi}) of the cloud, got {len(pts)}")
+        if out is None:
+            out = np.empty((hi - lo, 6), np.float32)
+        vp = None if viewpoint is None else np.ascontiguousarray(viewpoint, np.float32).reshape(3)
+        self.ctx.check(self.ctx.lib.tc_estimate_normals_distributed(
+            self.ctx.h, self.h, _vp(pts.ctypes.data), int(n_total), int(k),
+            1 if consistent_orientation else 0, None if vp is None else _vp(vp.ctypes.data),
+            _vp(out.ctypes.data)))
+        return out
 
     def allreduce_f64(self, dptr: int, count: int):
         self.ctx.check(self.ctx.lib.tc_comm_allreduce_f64(self.h, _vp(dptr), int(count)))

@@ -523,7 +523,7 @@ extern "C" int tc_estimate_normals_device(tc_context* ctx, const tc_index* ix, u
   TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (*h == 0) return TC_OK;
   tc_index* full = nullptr;
-  TC_TRY(tci_index_build(ctx, ix->cloud, ix->k_hint, ix->cell_size_arg, 0, 1, &full));
+  TC_TRY(tci_index_build(ctx, ix->cloud, ix->k_hint, 0.0f, 0, 1, &full, &ix->lv[0].g));
   int st = TC_OK;
   if (full->n_levels != 1 || full->lv[0].n_cells != ix->lv[0].n_cells) {
     st = tc_fail(ctx, TC_GPU, "sharded normals: the complete index chose a different grid");

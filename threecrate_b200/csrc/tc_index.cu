@@ -179,52 +179,87 @@ struct LevelJob {
   const uint32_t* cell_start;  // n_cells + 1 (scatter only)
   float4* out;                 // n (scatter only)
   uint32_t cell_lo, cell_hi;   // only cells in [cell_lo, cell_hi) take part (slab-sharded build)
+  // histogram only (slab build): the planes p of the slowest axis with p % sample == 0 (sample a
+  // power of two, 0: none) are ALSO counted, compactly, in sample_counts[(p / sample) * plane +
+  // offset in plane] - the statistics sample every rank takes alike
+  int sample;
+  uint32_t plane;              // cells per plane
+  uint32_t* sample_counts;
 };
 struct LevelJobs {
   int n;
   LevelJob l[kMaxLevels];
 };
 
-__device__ __forceinline__ uint32_t point_cell(const GridParams& g, float x, float y, float z) {
+__device__ __forceinline__ uint32_t point_cell(const GridParams& g, float x, float y, float z,
+                                               int* plane = nullptr) {
   float u;
   const int cx = cell_coord(x, g.ox, g.inv, g.nx, u);
   const int cy = cell_coord(y, g.oy, g.inv, g.ny, u);
   const int cz = cell_coord(z, g.oz, g.inv, g.nz, u);
+  if (plane) *plane = g.ymajor ? cy : cz;  // coordinate along the slowest axis
   return cell_id(g, cx, cy, cz);
+}
+
+// f(i, x, y, z) for every point, grid-stride.  A 16-byte aligned array is read four points (three
+// 128-bit loads) per thread and trip: a third of the load instructions, 48 bytes in flight.
+template <class F>
+__device__ __forceinline__ void for_each_point(const float* __restrict__ xyz, uint32_t n, F&& f) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  uint32_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+    const float4* v4 = reinterpret_cast<const float4*>(xyz);
+    const uint32_t groups = n / 4;
+    for (uint32_t gi = tid; gi < groups; gi += stride) {
+      const float4 a = __ldg(&v4[3 * (uint64_t)gi]), b = __ldg(&v4[3 * (uint64_t)gi + 1]),
+                   c = __ldg(&v4[3 * (uint64_t)gi + 2]);
+      f(4 * gi + 0, a.x, a.y, a.z);
+      f(4 * gi + 1, a.w, b.x, b.y);
+      f(4 * gi + 2, b.z, b.w, c.x);
+      f(4 * gi + 3, c.y, c.z, c.w);
+    }
+    done = 4 * groups;
+  }
+  for (uint32_t i = done + tid; i < n; i += stride)
+    f(i, xyz[3 * (uint64_t)i + 0], xyz[3 * (uint64_t)i + 1], xyz[3 * (uint64_t)i + 2]);
 }
 
 __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restrict__ xyz, uint32_t n,
                                                           const __grid_constant__ LevelJobs jobs) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float x = xyz[3 * (uint64_t)i + 0], y = xyz[3 * (uint64_t)i + 1],
-                z = xyz[3 * (uint64_t)i + 2];
+  for_each_point(xyz, n, [&](uint32_t, float x, float y, float z) {
     const uint32_t active = __activemask();
     for (int l = 0; l < jobs.n; ++l) {
-      const uint32_t c = point_cell(jobs.l[l].g, x, y, z);
-      const bool in = c >= jobs.l[l].cell_lo && c < jobs.l[l].cell_hi;
-      if (!jobs.l[l].aggregate) {  // more cells than points: plain reductions, no matching
-        if (in) atomicAdd(&jobs.l[l].counts[c], 1u);
+      const LevelJob& jb = jobs.l[l];
+      int plane;
+      const uint32_t c = point_cell(jb.g, x, y, z, &plane);
+      const bool in = c >= jb.cell_lo && c < jb.cell_hi;
+      if (jb.sample && (plane & (jb.sample - 1)) == 0)
+        atomicAdd(&jb.sample_counts[(uint64_t)(plane / jb.sample) * jb.plane +
+                                    (c - (uint32_t)plane * jb.plane)], 1u);
+      if (!jb.aggregate) {  // more cells than points: plain reductions, no matching
+        if (in) atomicAdd(&jb.counts[c], 1u);
         continue;
       }
       // warp-aggregated: consecutive points of a scan usually share a cell, and coarse levels
       // funnel thousands of points into one counter
       const uint32_t peers = __match_any_sync(active, c);
       if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && in)
-        atomicAdd(&jobs.l[l].counts[c], (uint32_t)__popc(peers));
+        atomicAdd(&jb.counts[c], (uint32_t)__popc(peers));
     }
-  }
+  });
 }
 
 // occupied cells, max population, points living in cells with population <= low_thr x {1,2,4,8}
-// (how much of the cloud is too sparse for this cell size) -> published at s[24..29]
+// (how much of the cloud is too sparse for this cell size), points counted -> host[8..14]
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
                                                          uint64_t n_cells, uint32_t low_thr,
                                                          uint32_t* __restrict__ s,
                                                          volatile uint32_t* host, uint32_t seq) {
-  uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0};
+  uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0}, tot = 0;
   auto upd = [&](uint32_t c) {
     occ += (c != 0);
     mx = max(mx, c);
+    tot += c;
 #pragma unroll
     for (int j = 0; j < 4; ++j) low[j] += (c <= (low_thr << j)) ? c : 0u;  // thresholds x1,2,4,8
   };
@@ -252,16 +287,18 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
   for (int o = 16; o > 0; o >>= 1) {
     occ += __shfl_xor_sync(0xffffffffu, occ, o);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) low[j] += __shfl_xor_sync(0xffffffffu, low[j], o);
   }
-  __shared__ uint32_t sred[kThreads / 32][6];  // per-warp partials -> six atomics per block
+  __shared__ uint32_t sred[kThreads / 32][7];  // per-warp partials -> seven atomics per block
   if ((threadIdx.x & 31) == 0) {
     uint32_t* r = sred[threadIdx.x >> 5];
     r[0] = occ;
     r[1] = mx;
 #pragma unroll
     for (int j = 0; j < 4; ++j) r[2 + j] = low[j];
+    r[6] = tot;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -270,12 +307,14 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
       mx = max(mx, sred[w][1]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) low[j] += sred[w][2 + j];
+      tot += sred[w][6];
     }
     if (occ) atomicAdd(&s[8], occ);
     if (mx) atomicMax(&s[9], mx);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (low[j]) atomicAdd(&s[10 + j], low[j]);
+    if (tot) atomicAdd(&s[15], tot);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -283,6 +322,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
     if (atomicAdd(&s[14], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
       __threadfence();
       for (int j = 0; j < 6; ++j) host[8 + j] = atomicExch(&s[8 + j], 0u);
+      host[14] = atomicExch(&s[15], 0u);
       s[14] = 0u;
       __threadfence_system();
       host[15] = seq;
@@ -294,23 +334,22 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
 // every level of `jobs`.  The order INSIDE a cell is arrival order (not deterministic) — nothing
 // downstream depends on it: every selection is keyed by (d2, original index) and multi-GPU
 // shards own whole cells.
-// (`zero` lists up to two word ranges nothing in this launch reads - the scan's tile states, an
-//  abandoned trial histogram - which are cleared here so the cached workspaces are left all zero)
+// (`zero` lists up to three word ranges nothing in this launch reads - the scan's tile states, an
+//  abandoned trial histogram, the statistics sample of a slab build - which are cleared here so
+//  the cached workspaces are left all zero)
 struct ZeroJobs {
-  uint32_t* p[2];
-  uint64_t n[2];
+  uint32_t* p[3];
+  uint64_t n[3];
 };
 __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __restrict__ xyz,
                                                              uint32_t n,
                                                              const __grid_constant__ LevelJobs jobs,
                                                              const ZeroJobs zero) {
-  for (int z = 0; z < 2; ++z)
+  for (int z = 0; z < 3; ++z)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero.n[z];
          i += (uint64_t)gridDim.x * blockDim.x)
       zero.p[z][i] = 0u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float x = xyz[3 * (uint64_t)i + 0], y = xyz[3 * (uint64_t)i + 1],
-                z = xyz[3 * (uint64_t)i + 2];
+  for_each_point(xyz, n, [&](uint32_t i, float x, float y, float z) {
     const float4 v = make_float4(x, y, z, __uint_as_float(i));
     const uint32_t active = __activemask();
     const int lane = threadIdx.x & 31;
@@ -336,27 +375,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __rest
         jb.out[pos] = v;
       }
     }
-  }
-}
-
-// Slab-sharded build: the cell table keeps its full length (kernels index it by global cell id),
-// but only [cell_lo, cell_hi] was scanned.  Cells in front of the slab get 0 and cells behind it
-// the slab's point count, so every range that leaves the slab is empty; the trial histogram's
-// counters outside the slab are cleared so the cached workspace is all zero again.
-__global__ void __launch_bounds__(kThreads) k_fill_outside(uint32_t* __restrict__ cs,
-                                                           uint32_t* __restrict__ counts,
-                                                           uint64_t n_cells, uint64_t cell_lo,
-                                                           uint64_t cell_hi) {
-  const uint32_t n_local = cs[cell_hi];
-  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = tid; i < cell_lo; i += stride) {
-    cs[i] = 0u;
-    if (counts) counts[i] = 0u;
-  }
-  for (uint64_t i = cell_hi + 1 + tid; i <= n_cells; i += stride) cs[i] = n_local;
-  if (counts)
-    for (uint64_t i = cell_hi + tid; i <= n_cells; i += stride) counts[i] = 0u;
+  });
 }
 
 // ---------------------------------------------------------------------- exclusive scan (u32)
@@ -792,30 +811,73 @@ namespace {
 inline uint64_t round_up4(uint64_t v) { return (v + 3) & ~(uint64_t)3; }
 inline uint64_t cells_of(const GridParams& g) { return (uint64_t)g.nx * g.ny * g.nz; }
 
+// Slab of a grid owned by `rank`: whole planes along the slowest axis, built with `halo` planes
+// on either side.
+struct Slab {
+  bool on = false;
+  uint64_t plane = 0;  // cells per plane
+  int n_planes = 0;
+  uint64_t cell_lo = 0, cell_hi = 0, own_cell_lo = 0, own_cell_hi = 0;
+};
+constexpr int kSamplePlanes = 8;  // the statistics sample of a slab build: every 8th plane
+Slab slab_of(const GridParams& g, int rank, int world, int halo) {
+  Slab s;
+  s.plane = g.ymajor ? (uint64_t)g.nz * g.nx : (uint64_t)g.ny * g.nx;
+  s.n_planes = g.ymajor ? g.ny : g.nz;
+  s.cell_hi = s.own_cell_hi = cells_of(g);
+  s.on = world > 1 && s.n_planes >= 4 * world;
+  if (s.on) {
+    const int p_lo = (int)((int64_t)rank * s.n_planes / world),
+              p_hi = (int)((int64_t)(rank + 1) * s.n_planes / world);
+    s.own_cell_lo = (uint64_t)p_lo * s.plane;
+    s.own_cell_hi = (uint64_t)p_hi * s.plane;
+    s.cell_lo = (uint64_t)std::max(p_lo - halo, 0) * s.plane;
+    s.cell_hi = (uint64_t)std::min(p_hi + halo, s.n_planes) * s.plane;
+  }
+  return s;
+}
+
+// the trial workspace: the histogram (n_cells + 1 counters), then the compact sample table
+inline uint64_t sample_off_of(const GridParams& g) { return round_up4(cells_of(g) + 1); }
+inline uint64_t sample_words_of(const Slab& s) {
+  return s.on ? (uint64_t)((s.n_planes + kSamplePlanes - 1) / kSamplePlanes) * s.plane : 0;
+}
+inline uint64_t trial_words_of(const GridParams& g, const Slab& s) {
+  return sample_off_of(g) + sample_words_of(s);
+}
+
 // Trial histogram of `cloud` on grid g plus its statistics (one host sync):
-// stats = occupied / max_pop / points in cells with population <= low_thr x {1,2,4,8}
+// stats = occupied / max_pop / points in cells with population <= low_thr x {1,2,4,8} / points
+// counted.  A slab build counts only the rank's slab, plus - in a compact table behind the
+// histogram - the sample planes (every rank the same ones, so every rank takes the same
+// decisions), and takes the statistics over the sample; the scatter launch clears the sample.
 int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g, uint32_t low_thr,
-                    uint32_t** d_counts_out, uint32_t stats[6]) {
+                    const Slab& slab, uint32_t** d_counts_out, uint32_t stats[7]) {
   const uint64_t n = cloud->n, n_cells = cells_of(g);
   uint32_t* d_counts = nullptr;
-  TC_TRY(tc_ws_get_zeroed(ctx, 0, &d_counts, n_cells + 1));
+  TC_TRY(tc_ws_get_zeroed(ctx, 0, &d_counts, trial_words_of(g, slab)));
   *d_counts_out = d_counts;
   LevelJobs jobs{};
   jobs.n = 1;
   jobs.l[0].g = g;
   jobs.l[0].counts = d_counts;
-  jobs.l[0].cell_lo = 0u;
-  jobs.l[0].cell_hi = 0xFFFFFFFFu;
+  jobs.l[0].cell_lo = slab.on ? (uint32_t)slab.cell_lo : 0u;
+  jobs.l[0].cell_hi = slab.on ? (uint32_t)slab.cell_hi : 0xFFFFFFFFu;
+  jobs.l[0].sample = slab.on ? kSamplePlanes : 0;
+  jobs.l[0].plane = (uint32_t)slab.plane;
+  jobs.l[0].sample_counts = d_counts + sample_off_of(g);
   jobs.l[0].aggregate = n_cells < n ? 1 : 0;
-  k_hist_levels<<<grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n,
-                                                                         jobs);
+  k_hist_levels<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(cloud->d_xyz,
+                                                                             (uint32_t)n, jobs);
   TC_LAUNCHED(ctx);
   const uint32_t seq = ++ctx->seq;
-  k_cell_stats<<<grid_for(ctx, n_cells, kThreads * 4), kThreads, 0, ctx->stream>>>(
-      d_counts, n_cells, low_thr, ctx->d_scratch, ctx->h_scratch, seq);
+  const uint32_t* d_stat = slab.on ? d_counts + sample_off_of(g) : d_counts;
+  const uint64_t n_stat = slab.on ? sample_words_of(slab) : n_cells;
+  k_cell_stats<<<grid_for(ctx, n_stat, kThreads * 4), kThreads, 0, ctx->stream>>>(
+      d_stat, n_stat, low_thr, ctx->d_scratch, ctx->h_scratch, seq);
   TC_LAUNCHED(ctx);
   TC_TRY(wait_host_flag(ctx, ctx->h_scratch + 15, seq));
-  for (int j = 0; j < 6; ++j) stats[j] = ctx->h_scratch[8 + j];
+  for (int j = 0; j < 7; ++j) stats[j] = ctx->h_scratch[8 + j];
   return TC_OK;
 }
 
@@ -842,7 +904,8 @@ extern "C" int tc_index_build_sharded(tc_context* ctx, const tc_cloud* cloud, ui
 }
 
 int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
-                    int rank, int world, tc_index** out) {
+                    int rank, int world, tc_index** out, const GridParams* like) {
+  if (like) cell_size = like->cell;  // same cell edge and cell order as an existing index
   TcRange nvtx_range("tc_index_build");
   if (!ctx || !cloud || !out) return TC_INVALID_DATA;
   *out = nullptr;
@@ -869,7 +932,8 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
     return TC_OK;
   }
   PhaseTrace trace(ctx);
-  g_make_grid_ymajor = world > 1;
+  g_make_grid_ymajor = like ? like->ymajor != 0 : world > 1;
+  const int halo = std::min(g_tc_shard_halo, 255);
   int st = tci_bbox(ctx, cloud->d_xyz, n, ix->bbox_min, ix->bbox_max);
   trace.mark("bbox");
   if (st != TC_OK) {
@@ -900,7 +964,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
     if (emax > 0 && cell > emax) cell = (float)emax;
     if (emax > 0 && cell < emax * 1e-6) cell = (float)(emax * 1e-6);
   }
-  uint32_t stats[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t stats[7] = {0, 0, 0, 0, 0, 0, 0};
   // One measured trial (histogram + stats + one host sync).  If the mean population of occupied
   // cells is off target the cell is rescaled ONCE (surface-like scaling: occupied ~ cell^-2) and
   // re-histogrammed together with the extra resolutions, without waiting for new statistics;
@@ -908,16 +972,20 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   float stat_scale = 1.0f;  // final cell / measured cell
   GridParams g = make_grid(mn, mx, cell, n, table_cap);
   cell = g.cell;
-  st = trial_histogram(ctx, cloud, g, low_thr, &d_trial, stats);
+  const Slab tslab = slab_of(g, rank, world, halo);  // (a slab build samples its statistics)
+  st = trial_histogram(ctx, cloud, g, low_thr, tslab, &d_trial, stats);
   trace.mark("trial histogram+stats");
   if (st != TC_OK) {
     tc_ws_release_zeroed(ctx, 0, d_trial, false);
     delete ix;
     return st;
   }
-  const uint64_t trial_words = cells_of(g) + 1;
+  const uint64_t trial_words = cells_of(g) + 1, trial_sample_off = sample_off_of(g);
   bool primary_counted = true;  // d_trial holds the primary histogram
-  const float pop1 = (float)n / (float)std::max(1u, stats[0]);
+  // points the statistics were taken over: all of them, or the sample planes of a slab build
+  const double samp_n = std::max<double>(1.0, (double)stats[6]);
+  const double samp_ratio = (double)n / samp_n;
+  const float pop1 = stats[0] ? (float)(samp_n / (double)stats[0]) : target;
   if (auto_cell && !(pop1 > target * 0.7f && pop1 < target * 1.4f)) {
     float scale = std::sqrt(target / pop1);
     scale = std::min(4.0f, std::max(0.25f, scale));
@@ -933,7 +1001,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   }
   // statistics of the final grid, extrapolated from the measured one when it was rescaled
   const float s2 = stat_scale * stat_scale;
-  const uint32_t occ_est = (uint32_t)std::max(1.0f, (float)stats[0] / s2);
+  const uint32_t occ_est = (uint32_t)std::max(1.0, (double)stats[0] * samp_ratio / s2);
   const uint32_t maxpop_est = (uint32_t)std::min<double>(
       (double)n, std::ceil((double)stats[1] * std::max(1.0f, s2 * stat_scale)));
   // skew of the measured trial: densest cell vs mean, and share of points in near-empty cells
@@ -949,7 +1017,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   // sits in nearly empty cells (far field: ring growth would otherwise walk thousands of rows).
   bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
   const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
-                           low_thr > 0 && (double)low_pts > 0.01 * (double)n && n > 4096;
+                           low_thr > 0 && (double)low_pts > 0.01 * samp_n && n > 4096;
 
   // Level geometry, finest first.
   GridParams lg[kMaxLevels];
@@ -979,19 +1047,16 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
     words += 4 * n;
   }
   // Slab-sharded build (one resolution, slabs of whole planes along the slowest axis): this
-  // rank scans / scatters only the cells of its planes +- g_tc_shard_halo.
-  const uint64_t plane = lg[0].ymajor ? (uint64_t)lg[0].nz * lg[0].nx : (uint64_t)lg[0].ny * lg[0].nx;
-  const int n_planes = lg[0].ymajor ? lg[0].ny : lg[0].nz;
-  const bool slab = world > 1 && nl == 1 && n_planes >= 4 * world;
-  uint64_t cell_lo = 0, cell_hi = cells_of(lg[0]), own_cell_lo = 0, own_cell_hi = cell_hi;
-  if (slab) {
-    const int p_lo = (int)((int64_t)rank * n_planes / world),
-              p_hi = (int)((int64_t)(rank + 1) * n_planes / world);
-    own_cell_lo = (uint64_t)p_lo * plane;
-    own_cell_hi = (uint64_t)p_hi * plane;
-    cell_lo = (uint64_t)std::max(p_lo - g_tc_shard_halo, 0) * plane;
-    cell_hi = (uint64_t)std::min(p_hi + g_tc_shard_halo, n_planes) * plane;
-  }
+  // rank scans / scatters only the cells of its planes +- halo.  Nothing outside the slab is
+  // written or read: the search's ring cap (GridParams.flags bits 8..15) keeps it inside.
+  Slab slab_off;
+  slab_off.cell_hi = slab_off.own_cell_hi = cells_of(lg[0]);
+  const Slab sl = nl == 1 ? slab_of(lg[0], rank, world, halo) : slab_off;
+  const bool slab = sl.on;
+  const uint64_t cell_lo = sl.cell_lo, cell_hi = sl.cell_hi, own_cell_lo = sl.own_cell_lo,
+                 own_cell_hi = sl.own_cell_hi;
+  // a sampled trial histogram is complete only inside the slab it was taken for
+  if (tslab.on && primary_counted && !slab) primary_counted = false;
   uint64_t twords = 0, cnt_off[kMaxLevels], tiles = 0;
   for (int l = 0; l < nl; ++l) {
     tiles += (cells_of(lg[l]) + kScanTile - 1) / kScanTile;
@@ -1038,7 +1103,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
       scan.out[l] = ix->d_arena + cs_off[l] + (slab ? cell_lo : 0);
       scan.len[l] = slab ? cell_hi - cell_lo : cells_of(lg[l]);
     }
-    const int grid = grid_for(ctx, n, kThreads);
+    const int grid = grid_for(ctx, n, kThreads * 4);  // (four points per thread and trip)
     if (todo.n > 0) {
       k_hist_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, todo);
       ctx->launches++;
@@ -1050,28 +1115,26 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
       ZeroJobs zero{};
       zero.p[0] = d_tmp + state_off;
       zero.n[0] = twords - state_off;
-      zero.p[1] = d_trial;
-      zero.n[1] = primary_counted ? 0 : trial_words;
+      zero.p[1] = d_trial + (tslab.on ? tslab.cell_lo : 0);
+      zero.n[1] = primary_counted ? 0 : tslab.on ? tslab.cell_hi - tslab.cell_lo + 1 : trial_words;
+      zero.p[2] = d_trial + trial_sample_off;  // the statistics sample of a slab build
+      zero.n[2] = sample_words_of(tslab);
       k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all, zero);
       ctx->launches++;
       trace.mark("launches: hist/scan/scatter");
       if (slab) {
-        // table entries outside the slab (and the trial histogram's leftover counters there)
-        k_fill_outside<<<grid_for(ctx, cells_of(lg[0]), kThreads * 4), kThreads, 0, ctx->stream>>>(
-            ix->d_arena + cs_off[0], all.l[0].counts, cells_of(lg[0]), cell_lo, cell_hi);
-        ctx->launches++;
         // the rank's own query range and point count, in local sorted positions
         const uint32_t* cs = ix->d_arena + cs_off[0];
         uint32_t* h = ctx->h_scratch + 44;
         cudaMemcpyAsync(h + 0, cs + own_cell_lo, 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(h + 1, cs + own_cell_hi, 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(h + 2, cs + cell_hi, 4, cudaMemcpyDeviceToHost, ctx->stream);
-        trace.mark("slab: fill + readback enqueued");
+        trace.mark("slab: readback enqueued");
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
           st = tc_fail(ctx, TC_GPU, "sharded index build failed");
         trace.mark("slab: stream sync");
         ix->sharded = true;
-        ix->shard_halo = g_tc_shard_halo;
+        ix->shard_halo = halo;
         ix->cell_lo = cell_lo;
         ix->cell_hi = cell_hi;
         ix->own_cell_lo = own_cell_lo;

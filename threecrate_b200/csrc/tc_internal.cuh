@@ -42,6 +42,13 @@ struct tc_context {
   void* ws[kWsSlots] = {nullptr, nullptr, nullptr};
   uint64_t ws_bytes[kWsSlots] = {0, 0, 0};
   bool ws_zero[kWsSlots] = {false, false, false};  // cached buffer known to be all zero
+  // distributed normals (tc_estimate_normals_distributed): while chunk != 0 the normals kernels
+  // write row i into the buffer of the rank that owns original index i (i / chunk), over NVLink
+  // peer memory; base[r] is pre-offset so that base[r] + 6 i is row i of rank r's chunk
+  struct OutRoute {
+    float* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t chunk = 0, magic = 0;  // magic = floor(2^32 / chunk)
+  } route;
 };
 
 struct tc_cloud {
@@ -85,6 +92,10 @@ struct LevelSet {
   // points of the unbuilt part and is counted in *unsafe (the caller then re-runs unsharded)
   int halo;            // 0: complete index
   uint32_t* unsafe;
+  // output routing of the distributed normals (tc_context::OutRoute); chunk == 0: rows go to the
+  // launch's own output buffer
+  float* route[8];
+  uint32_t route_chunk, route_magic;
 };
 
 struct tc_index {
@@ -112,9 +123,13 @@ struct tc_index {
     s.n = n_levels;
     s.halo = sharded ? shard_halo : 0;
     s.unsafe = sharded ? ctx->d_scratch + 42 : nullptr;
+    for (int r = 0; r < 8; ++r) s.route[r] = ctx->route.base[r];
+    s.route_chunk = ctx->route.chunk;
+    s.route_magic = ctx->route.magic;
     for (int i = 0; i < n_levels; ++i) {
       s.g[i] = lv[i].g;
-      s.g[i].flags = flags;
+      // bits 8..15: ring cap of a slab-sharded index (grid_search never reads unbuilt cells)
+      s.g[i].flags = (flags & 255) | (sharded ? (shard_halo & 255) << 8 : 0);
       s.pts[i] = lv[i].d_pts;
       s.cs[i] = lv[i].d_cell_start;
     }
@@ -242,8 +257,9 @@ int tci_knn_launch(tc_context* ctx, const tc_index* index, const float4* d_queri
 int tci_normals_launch(tc_context* ctx, const tc_index* index, uint32_t k, int orient,
                        const float vp[3], uint64_t q_begin, uint64_t q_end, float* d_out_aos,
                        bool exact_range = false);
+// like != nullptr: a complete index with the cell edge and cell order of an existing grid
 int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, float cell_size,
-                    int rank, int world, tc_index** out);
+                    int rank, int world, tc_index** out, const GridParams* like = nullptr);
 int tci_normals_radius_launch(tc_context* ctx, const tc_index* index, float radius, uint32_t k,
                               int orient, const float vp[3], uint64_t q_begin, uint64_t q_end,
                               float* d_out_aos);

@@ -328,7 +328,8 @@ k_normals(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint32_t
     int level;
     const int R = level_search(ls, q.x, q.y, q.z, k + 1, tk, level);
     if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
-    normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz, out);
+    normals_emit(RegKeys<K>{tk.key, xyz}, q, qid, k, orient, vpx, vpy, vpz,
+                 route_out(ls, qid, out));
     TC_DBG(if (dbg) {  // per-query cycles and final block radius (tools/qclock.py)
       dbg[8 * (size_t)qid] = (uint32_t)(clock64() - t0);
       dbg[8 * (size_t)qid + 1] = (uint32_t)R | ((uint32_t)level << 16);
@@ -369,7 +370,7 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
   }
   if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
-               out, (ls.g[0].flags & 128) != 0);
+               route_out(ls, qid, out), (ls.g[0].flags & 128) != 0);
   TC_DBG(if (dbg) {
     dbg[0] = (uint32_t)(clock64() - t0);
     dbg[1] = (uint32_t)n | ((uint32_t)level << 16);
@@ -632,7 +633,7 @@ k_normals_big(LevelSet ls, const float* __restrict__ xyz, uint32_t q_begin, uint
   if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);
   hk.sort_ascending();
   normals_emit(GlobalKeys{hk.h, (int)hk.n, xyz}, q, __float_as_uint(q.w), k, orient, vpx, vpy, vpz,
-               out);
+               route_out(ls, __float_as_uint(q.w), out));
 }
 
 constexpr uint32_t kBigChunk = 1u << 18;  // queries per launch of the any-k kernels (heap memory)
@@ -737,7 +738,8 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
   k_knn2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,   \
                                                    (uint32_t)q_end, k, need, drop_self,       \
                                                    d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)
-  if (flags & 32) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
+  if ((flags & 32) && !ix->sharded) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
     uint32_t* d_stats = nullptr;
     ctx->stats_queries = nq;
     if (ctx->stats_on) {
@@ -818,7 +820,8 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
   k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
       ls, (uint32_t)q_begin, (uint32_t)q_end, own_begin, own_end, k, orient, vp[0], vp[1],   \
       vp[2], d_out_aos, d_fb + 1, d_fb TC_DBG_ARG(g_tc_dbg))
-  if (flags & 32) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
+  if ((flags & 32) && !ix->sharded) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
     uint32_t* d_stats = nullptr;
     ctx->stats_queries = nq;
     if (ctx->stats_on) {

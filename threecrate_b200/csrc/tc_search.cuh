@@ -372,8 +372,18 @@ __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __
     // escalate to a coarser level only while the block does not even hold K points (sparse
     // neighbourhood); a full list that is not yet provably final needs just another ring here
     if (R >= max_R && !tk.full()) break;
+    const int Rn = tk.full() ? R + 1 : 2 * R;
+    // slab-sharded index (flags bits 8..15 = halo planes): cells beyond the halo are not built, so
+    // the search stops here and reports a radius past the halo - the caller counts the query as
+    // unsafe and its row is redone on a complete index
+    const int r_cap = (flags >> 8) & 255;
+    if (r_cap && Rn > r_cap) {
+      done = true;
+      R = r_cap + 1;
+      break;
+    }
     Rp = R;
-    R = tk.full() ? R + 1 : 2 * R;
+    R = Rn;
   }
   return R;
 }
@@ -524,6 +534,16 @@ __device__ __forceinline__ void box_visit(const GridParams& g, const uint32_t* _
       const uint32_t hi = __ldg(&cell_start[row + xb + 1]);
       f(lo, hi);
     }
+}
+
+// Where the row of original index `qid` goes: the launch's own buffer, or (distributed normals)
+// the chunk buffer of rank qid / chunk.  __umulhi(qid, floor(2^32 / chunk)) is the quotient or
+// one below it.
+__device__ __forceinline__ float* route_out(const LevelSet& ls, uint32_t qid, float* out) {
+  if (ls.route_chunk == 0) return out;
+  uint32_t r = __umulhi(qid, ls.route_magic);
+  if ((r + 1) * ls.route_chunk <= qid) ++r;
+  return ls.route[r];
 }
 
 }  // namespace tcs
