@@ -893,6 +893,19 @@ def bench_c5(E):
         index.free()
     ms_index = float(np.mean([x[0] for x in res]))
     ms_icp = E.max_over_ranks(float(np.mean([x[1] for x in res])))
+    # where the time goes: the same call stopped after 1, 2, 3, 5 and 10 iterations
+    cumulative = {}
+    index = tc.GridIndex(tcloud, k_hint=1)
+    for it in (1, 2, 3, 5, 10):
+        E.barrier()
+        e1, e2 = E.ev(), E.ev()
+        e1.record(ext)
+        tc.icp_point_to_plane_device(scloud, index, nrm.data_ptr(), tc.IDENTITY, it, None, -1.0, comm)
+        e2.record(ext)
+        ctx.synchronize()
+        cumulative[str(it)] = round(E.max_over_ranks(e1.elapsed_time(e2)), 3)
+    cumulative[str(iters)] = round(ms_icp, 3)
+    index.free()
     scloud.free()
     tcloud.free()
     if comm:
@@ -904,7 +917,7 @@ def bench_c5(E):
         "iterations": iters, "n_gpus": E.world, "timed_reps": steps,
         "iters_per_s": iters / (ms_icp * 1e-3), "ms_per_iter": ms_icp / iters,
         "source_points_per_s": ns * E.world * iters / (ms_icp * 1e-3),
-        "ms_index_build_100m": ms_index,
+        "ms_index_build_100m": ms_index, "cumulative_ms_after_iterations": cumulative,
         "scaling": "weak in the source (12.5M points per rank = one of 8 spatial slabs of the "
                    "100M-point source), target + grid replicated; N = 8 is BASELINE config 5 "
                    "(100M <-> 100M)",

@@ -55,6 +55,15 @@ struct V3 {
   float x, y, z;
 };
 
+// Level of a multi-resolution target index for a query whose nearest candidate so far is sqrt(d2)
+// away: the finest one on which that is at most four cells (a box or ring search then touches
+// tens of rows, not thousands); the coarsest otherwise.
+__device__ __forceinline__ int pick_level(const LevelSet& ls, float d2) {
+  int l = 0;
+  while (l < ls.n - 1 && !(d2 <= 16.0f * ls.g[l].cell * ls.g[l].cell)) ++l;
+  return l;
+}
+
 // Fused all-reduce over NVLink peer memory (tc_comm peer exchange, tc_comm.cu): every rank's
 // exchange buffer is IPC-mapped into all ranks.  slot(parity, src) = base + (parity*world+src)*32
 // doubles: [0..28] payload, [31] epoch flag.
@@ -204,6 +213,16 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         }
       }
       if (!keep) {
+        // Every search starts on the finest level (the probe and the box query are cheapest
+        // there); only a candidate that is still several cells away after the probe moves the
+        // search to a coarser level (pick_level, below).  A candidate found on another level
+        // keeps its distance as the bound, but its position belongs to that level's array: its
+        // key is raised by one, so the same point - met again on the new level, inside the ball
+        // that is searched in full - replaces it with the position there.
+        if (best.seeded && start != 0) {
+          best.key += 1;
+          start = 0;
+        }
         // Seeded (level << 30 | position of last iteration's match): a box query around the seed
         // distance - one or two rows of one or two cells once the pose has settled.  Without a
         // seed (first iteration), or when the pose jumped and the old match is cells away (second
@@ -249,7 +268,16 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
         const bool far = !best.full() || best.kth() > 16.0f * g.cell * g.cell;
         if (far) {
           const bool have = best.full();
-          if (have) best.seeded = true;  // keep the candidate in hand as the pruning bound
+          if (have) {
+            best.seeded = true;  // keep the candidate in hand as the pruning bound
+            if (ls.n > 1) {      // (a far candidate: continue on the level that suits its distance)
+              const int tl = pick_level(ls, best.kth());
+              if (tl != level) {
+                best.key += 1;
+                level = tl;
+              }
+            }
+          }
           level_search(ls, s.x, s.y, s.z, 1u, best, level, have ? level : -1);
           if (have && best.full()) covered = sqrtf(best.kth());
         } else {

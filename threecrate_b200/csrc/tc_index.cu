@@ -1016,8 +1016,11 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   // over target (dense LiDAR near field), a 4x coarser one when a visible share of the points
   // sits in nearly empty cells (far field: ring growth would otherwise walk thousands of rows).
   bool want_fine = auto_cell && g_tc_max_levels > 1 && skew > target_ratio && n > 4096;
-  const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) &&
-                           low_thr > 0 && (double)low_pts > 0.01 * samp_n && n > 4096;
+  // ... and always for a 1-NN index (k_hint <= 1: an ICP target): the first iterations of a badly
+  // aligned pair query it from several cells away, where the fine grid is thousands of empty
+  // rows and the coarse one a handful (tc_icp.cu picks the level by the distance in hand)
+  const bool want_coarse = auto_cell && g_tc_max_levels > (want_fine ? 2 : 1) && n > 4096 &&
+                           ((low_thr > 0 && (double)low_pts > 0.01 * samp_n) || k_hint <= 1);
 
   // Level geometry, finest first.
   GridParams lg[kMaxLevels];

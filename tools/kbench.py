@@ -21,6 +21,8 @@ ap.add_argument("--c4k", default="30")
 ap.add_argument("--cellscale", default="1.0")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--finecap", type=int, default=0)
+ap.add_argument("--iters", default="30", help="c3: comma list of iteration counts to time")
+ap.add_argument("--maxlevels", type=int, default=0, help="cap the index resolutions (1: no coarse/fine level)")
 a = ap.parse_args()
 ctx = tc.default_context()
 lib = _lib.load()
@@ -87,6 +89,9 @@ def normals_case(name, pts, k):
     ctx.free(d_out)
 
 
+if a.maxlevels:
+    lib.tc_debug_set_max_levels.argtypes = [C.c_int]
+    lib.tc_debug_set_max_levels(a.maxlevels)
 what = a.what.split(",")
 if "c2" in what:
     normals_case("c2", synth.kitti_frame(), 16)
@@ -112,8 +117,13 @@ if "c3" in what:
             setflags(f & 0xFFFF)
             lib.tc_debug_set_icp_keep(0 if (f >> 16) & 1 else 1)   # flag bit 16: search every time
             res = []
+            for it in [int(x) for x in a.iters.split(",")][:-1]:
+                ms = timed(lambda: res.append(tc.icp_point_to_plane_device(
+                    scloud, index, d_nrm, tc.IDENTITY, it, None, -1.0)), 3)
+                print(f"   iters={it}: {ms:8.3f} ms", flush=True)
+            res = []
             ms = timed(lambda: res.append(tc.icp_point_to_plane_device(
-                scloud, index, d_nrm, tc.IDENTITY, 30, None, -1.0)), 3)
+                scloud, index, d_nrm, tc.IDENTITY, int(a.iters.split(",")[-1]), None, -1.0)), 3)
             r = res[-1]
             if ref is None:
                 ref = r.transformation
