@@ -252,13 +252,13 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
             const uint32_t row = cell_id(g, 0, y, z);
             scan(__ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]));
           }
-          probed = !best.seeded;  // (a far seed may lie outside the probed rows: not "all scanned")
           px0 = x0;
           px1 = x1;
           py0 = min(cy, y2);
           py1 = max(cy, y2);
           pz0 = min(cz, z2);
           pz1 = max(cz, z2);
+          probed = !best.seeded;  // (a far seed may lie outside the probed rows: not "all scanned")
         }
         // Nothing in hand (the probe found no point), or the match is more than four cells away
         // (first iterations of a badly aligned pair): the ring search grows cell by cell from the

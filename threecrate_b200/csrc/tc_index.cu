@@ -1035,7 +1035,15 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   }
   primary = nl;
   lg[nl++] = g;
-  if (want_coarse) lg[nl++] = make_grid(mn, mx, g.cell * 4.0f, n, table_cap);
+  if (want_coarse) {
+    // 4x for sparse regions of a kNN index (ring growth there walks thousands of empty rows);
+    // 3x for the far queries of a 1-NN index, where the coarse cells' points are all candidates
+    // (measured on the 100M-point ICP target: 2x 300, 3x 294, 4x 233, 6x 200 iterations/s, and
+    // the build grows with the table: 27.0 / 24.1 / 22.5 / 21.4 ms)
+    float f = (low_thr > 0 && (double)low_pts > 0.01 * samp_n) ? 4.0f : 3.0f;
+    if (const char* e = std::getenv("TC_COARSE_FACTOR")) f = std::max(1.5f, (float)atof(e));  // (debug)
+    lg[nl++] = make_grid(mn, mx, g.cell * f, n, table_cap);
+  }
 
   // One persistent arena (cell_start tables + sorted points of every level) and one temporary
   // arena (histograms still to be counted + scan state), cleared by a single memset: every API
