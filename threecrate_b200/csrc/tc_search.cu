@@ -34,6 +34,45 @@ namespace {
 constexpr int kBlock = 128;
 using namespace tcs;
 
+// More candidates at or below the K-th squared distance than the member table holds: bit-equal
+// d2 straddling rank `need` (a handful of queries per million on real-valued data, every query
+// of a cloud with duplicated points).  The members are then collected exactly, in place: first
+// everything strictly below tau (fewer than `need` by the definition of tau), then the points AT
+// tau in ascending original index - one traversal per slot still open, each taking the smallest
+// index above the last one taken.  Not inlined: this is the cold path of the selection, and the
+// extra traversals would otherwise sit in the hot kernels' instruction stream.
+__device__ __noinline__ uint32_t resolve_ties(const GridParams g, const uint32_t* __restrict__ cell_start,
+                                              const float4* __restrict__ pts, float qx, float qy,
+                                              float qz, int R, float tau, uint32_t need,
+                                              uint32_t* col /* s_a[.][thread], stride kBlock */) {
+  uint32_t n = 0;
+  grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t j = lo; j < hi; ++j) {
+      const float4 c = __ldg(&pts[j]);
+      if (dist2_exact(c.x, c.y, c.z, qx, qy, qz) < tau) col[(n++) * kBlock] = j;
+    }
+  });
+  long long last = -1;
+  while (n < need) {
+    long long pick = 1ll << 40;
+    uint32_t pick_j = 0;
+    grid_visit(g, cell_start, qx, qy, qz, R, tau, [&](uint32_t lo, uint32_t hi) {
+      for (uint32_t j = lo; j < hi; ++j) {
+        const float4 c = __ldg(&pts[j]);
+        const long long id = (long long)__float_as_uint(c.w);
+        if (dist2_exact(c.x, c.y, c.z, qx, qy, qz) == tau && id > last && id < pick) {
+          pick = id;
+          pick_j = j;
+        }
+      }
+    });
+    if (pick == (1ll << 40)) break;  // (no point left at tau)
+    col[(n++) * kBlock] = pick_j;
+    last = pick;
+  }
+  return n;
+}
+
 // Two-pass exact selection for one query (see k_knn2).  On success the sorted positions (into
 // `pts`) of the neighbours, ascending by (d2, index), are in s_b[0 .. n)[threadIdx.x] and n is
 // returned; -1 means "ties: use the exact chain kernel" (bit-equal d2 inside the list, or more
@@ -50,8 +89,11 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
   constexpr int T = SelF<L, X>::kSlots;  // rows of s_a / s_b
   SelF<L, X> sel;
   sel.pad = T - (int)need;
-  const int R = level_search(ls, qx, qy, qz, need, sel, level);
+  int R = level_search(ls, qx, qy, qz, need, sel, level);
   if (R_out) *R_out = R;
+  // (slab-sharded index: a search stopped at the ring cap reports cap + 1 - the caller counts the
+  //  query as unsafe - but the second traversal must stay inside the built planes as well)
+  if (ls.halo && R > ls.halo) R = ls.halo;
   const GridParams& g = ls.g[level];
   const float4* __restrict__ pts = ls.pts[level];
   const uint32_t* __restrict__ cell_start = ls.cs[level];
@@ -71,7 +113,8 @@ __device__ __forceinline__ int select_two_pass(const LevelSet& ls, float qx, flo
       }
     }
   });
-  if (n > (uint32_t)T) return -1;  // more ties than the table holds: exact chain kernel instead
+  if (n > (uint32_t)T)  // more ties at tau than the table holds: resolved in place (cold path)
+    n = resolve_ties(g, cell_start, pts, qx, qy, qz, R, tau, need, &s_a[0][threadIdx.x]);
   // rank placement.  A member whose d2 is unique lands at #{v[i] < d2}.  Bit-equal d2 (inside
   // the list, or at the K-th distance when more than `need` points are at or below it) are
   // ordered by original index: such a member also counts the equal members with a smaller index.

@@ -14,7 +14,7 @@ import threecrate_b200 as tc
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 world = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-reps = 8
+reps = int(os.environ.get("REPS", "8"))
 pts = bench.head_cloud(n)
 ctx = tc.default_context()
 cloud = tc.DeviceCloud(pts, ctx)
