@@ -43,10 +43,13 @@ extern "C" int tc_context_create(int device, tc_context** out) {
     return fail("cudaEventCreate");
 
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (cudaMalloc((void**)&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
+  if (cudaMalloc((void**)&ctx->d_scratch, tc_context::kScratchWords * sizeof(uint32_t)) != cudaSuccess)
     return fail("cudaMalloc");
-  if (cudaMallocHost((void**)&ctx->h_scratch, 64 * sizeof(uint32_t)) != cudaSuccess)
+  if (cudaMallocHost((void**)&ctx->h_scratch, tc_context::kScratchWords * sizeof(uint32_t)) != cudaSuccess)
     return fail("cudaMallocHost");
+  if (cudaMalloc((void**)&ctx->d_planes, (size_t)tc_context::kPlaneWords * tc_context::kPlaneStride *
+                                             sizeof(uint32_t)) != cudaSuccess)
+    return fail("cudaMalloc");
   if (tci_scratch_arm(ctx) != TC_OK) return fail("scratch init");
   // keep freed blocks cached in the stream-ordered pool: no cudaMalloc/cudaFree per call
   cudaMemPool_t pool;
@@ -71,6 +74,7 @@ extern "C" void tc_context_destroy(tc_context* ctx) {
   for (int i = 0; i < tc_context::kArenaSlots; ++i)
     if (ctx->arena_cache[i]) cudaFree(ctx->arena_cache[i]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_planes) cudaFree(ctx->d_planes);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -16,6 +16,8 @@
 #include <chrono>
 #include <cstdlib>
 
+#include <vector>
+
 #include "tc_internal.cuh"
 
 namespace {
@@ -185,6 +187,11 @@ struct LevelJob {
   int sample;
   uint32_t plane;              // cells per plane
   uint32_t* sample_counts;
+  // ... and EVERY point is counted by its plane (block-private shared-memory histogram, one
+  // global atomic per plane and block): the ranks cut the cloud into slabs of equal point
+  // counts from these, every rank alike.  nullptr: off (more planes than the table holds).
+  uint32_t* plane_counts;
+  int n_planes;
 };
 struct LevelJobs {
   int n;
@@ -226,6 +233,12 @@ __device__ __forceinline__ void for_each_point(const float* __restrict__ xyz, ui
 
 __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restrict__ xyz, uint32_t n,
                                                           const __grid_constant__ LevelJobs jobs) {
+  __shared__ uint32_t s_planes[tc_context::kPlaneWords];
+  uint32_t* const plane_counts = jobs.l[0].plane_counts;  // (slab trial: one level)
+  if (plane_counts) {
+    for (int p = threadIdx.x; p < jobs.l[0].n_planes; p += kThreads) s_planes[p] = 0u;
+    __syncthreads();
+  }
   for_each_point(xyz, n, [&](uint32_t, float x, float y, float z) {
     const uint32_t active = __activemask();
     for (int l = 0; l < jobs.n; ++l) {
@@ -233,6 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
       int plane;
       const uint32_t c = point_cell(jb.g, x, y, z, &plane);
       const bool in = c >= jb.cell_lo && c < jb.cell_hi;
+      if (jb.plane_counts) atomicAdd(&s_planes[plane], 1u);
       if (jb.sample && (plane & (jb.sample - 1)) == 0)
         atomicAdd(&jb.sample_counts[(uint64_t)(plane / jb.sample) * jb.plane +
                                     (c - (uint32_t)plane * jb.plane)], 1u);
@@ -247,6 +261,11 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
         atomicAdd(&jb.counts[c], (uint32_t)__popc(peers));
     }
   });
+  if (plane_counts) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < jobs.l[0].n_planes; p += kThreads)
+      if (s_planes[p]) atomicAdd(&plane_counts[p * tc_context::kPlaneStride], s_planes[p]);
+  }
 }
 
 // occupied cells, max population, points living in cells with population <= low_thr x {1,2,4,8}
@@ -254,7 +273,9 @@ __global__ void __launch_bounds__(kThreads) k_hist_levels(const float* __restric
 __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restrict__ counts,
                                                          uint64_t n_cells, uint32_t low_thr,
                                                          uint32_t* __restrict__ s,
-                                                         volatile uint32_t* host, uint32_t seq) {
+                                                         volatile uint32_t* host, uint32_t seq,
+                                                         uint32_t* __restrict__ planes,
+                                                         int n_planes /* 0: none to publish */) {
   uint32_t occ = 0, mx = 0, low[4] = {0, 0, 0, 0}, tot = 0;
   auto upd = [&](uint32_t c) {
     occ += (c != 0);
@@ -317,16 +338,25 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
     if (tot) atomicAdd(&s[15], tot);
   }
   __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&s[14], 1u) == gridDim.x - 1) {  // last block: publish and re-arm
-      __threadfence();
-      for (int j = 0; j < 6; ++j) host[8 + j] = atomicExch(&s[8 + j], 0u);
-      host[14] = atomicExch(&s[15], 0u);
-      s[14] = 0u;
-      __threadfence_system();
-      host[15] = seq;
-    }
+    s_last = atomicAdd(&s[14], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last block: publish and re-arm (the per-plane counts of a slab build: all threads)
+  __threadfence();
+  for (int p = threadIdx.x; p < n_planes; p += kThreads)
+    host[64 + p] = atomicExch(&planes[p * tc_context::kPlaneStride], 0u);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < 6; ++j) host[8 + j] = atomicExch(&s[8 + j], 0u);
+    host[14] = atomicExch(&s[15], 0u);
+    s[14] = 0u;
+    __threadfence_system();
+    host[15] = seq;
   }
 }
 
@@ -338,14 +368,14 @@ __global__ void __launch_bounds__(kThreads) k_cell_stats(const uint32_t* __restr
 //  abandoned trial histogram, the statistics sample of a slab build - which are cleared here so
 //  the cached workspaces are left all zero)
 struct ZeroJobs {
-  uint32_t* p[3];
-  uint64_t n[3];
+  uint32_t* p[5];
+  uint64_t n[5];
 };
 __global__ void __launch_bounds__(kThreads) k_scatter_levels(const float* __restrict__ xyz,
                                                              uint32_t n,
                                                              const __grid_constant__ LevelJobs jobs,
                                                              const ZeroJobs zero) {
-  for (int z = 0; z < 3; ++z)
+  for (int z = 0; z < 5; ++z)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero.n[z];
          i += (uint64_t)gridDim.x * blockDim.x)
       zero.p[z][i] = 0u;
@@ -715,6 +745,10 @@ int tci_radix_sort_pairs(tc_context* ctx, uint32_t* d_keys, uint32_t* d_vals, ui
 int tci_scratch_arm(tc_context* ctx) {
   k_scratch_init<<<1, 64, 0, ctx->stream>>>(ctx->d_scratch);
   TC_LAUNCHED(ctx);
+  TC_CUDA(ctx, cudaMemsetAsync(ctx->d_planes, 0,
+                               (size_t)tc_context::kPlaneWords * tc_context::kPlaneStride *
+                                   sizeof(uint32_t),
+                               ctx->stream));
   return TC_OK;
 }
 
@@ -820,21 +854,48 @@ struct Slab {
   uint64_t cell_lo = 0, cell_hi = 0, own_cell_lo = 0, own_cell_hi = 0;
 };
 constexpr int kSamplePlanes = 8;  // the statistics sample of a slab build: every 8th plane
-Slab slab_of(const GridParams& g, int rank, int world, int halo) {
+// own planes [p_lo, p_hi) of the slowest axis, built with `halo` planes on either side
+Slab slab_planes(const GridParams& g, int world, int p_lo, int p_hi, int halo) {
   Slab s;
   s.plane = g.ymajor ? (uint64_t)g.nz * g.nx : (uint64_t)g.ny * g.nx;
   s.n_planes = g.ymajor ? g.ny : g.nz;
   s.cell_hi = s.own_cell_hi = cells_of(g);
   s.on = world > 1 && s.n_planes >= 4 * world;
   if (s.on) {
-    const int p_lo = (int)((int64_t)rank * s.n_planes / world),
-              p_hi = (int)((int64_t)(rank + 1) * s.n_planes / world);
     s.own_cell_lo = (uint64_t)p_lo * s.plane;
     s.own_cell_hi = (uint64_t)p_hi * s.plane;
     s.cell_lo = (uint64_t)std::max(p_lo - halo, 0) * s.plane;
     s.cell_hi = (uint64_t)std::min(p_hi + halo, s.n_planes) * s.plane;
   }
   return s;
+}
+inline int equal_boundary(int n_planes, int world, int r) { return (int)((int64_t)r * n_planes / world); }
+// slabs of equal plane counts
+Slab slab_of(const GridParams& g, int rank, int world, int halo) {
+  const int n_planes = g.ymajor ? g.ny : g.nz;
+  return slab_planes(g, world, equal_boundary(n_planes, world, rank),
+                     equal_boundary(n_planes, world, rank + 1), halo);
+}
+// how far a slab boundary may move away from the equal-planes position to balance the ranks'
+// point counts (the trial histogram counts that many planes more on either side)
+inline int balance_margin(int n_planes, int world) { return n_planes / world / 8; }
+// Boundaries that give every rank the same number of POINTS (per-plane counts of the whole cloud,
+// identical on every rank), each kept within `margin` planes of its equal-planes position.
+void balanced_boundaries(const uint32_t* plane_counts, int n_planes, uint64_t n, int world,
+                         int margin, int* bnd /* world + 1 */) {
+  bnd[0] = 0;
+  bnd[world] = n_planes;
+  uint64_t cum = 0;
+  int r = 1;
+  for (int p = 0; p < n_planes && r < world; ++p) {
+    cum += plane_counts[p];
+    while (r < world && cum * (uint64_t)world >= (uint64_t)r * n) bnd[r++] = p + 1;
+  }
+  for (; r < world; ++r) bnd[r] = n_planes;
+  for (r = 1; r < world; ++r) {
+    const int e = equal_boundary(n_planes, world, r);
+    bnd[r] = std::max(e - margin, std::min(e + margin, bnd[r]));
+  }
 }
 
 // the trial workspace: the histogram (n_cells + 1 counters), then the compact sample table
@@ -866,6 +927,9 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   jobs.l[0].sample = slab.on ? kSamplePlanes : 0;
   jobs.l[0].plane = (uint32_t)slab.plane;
   jobs.l[0].sample_counts = d_counts + sample_off_of(g);
+  const bool planes = slab.on && slab.n_planes <= tc_context::kPlaneWords;
+  jobs.l[0].plane_counts = planes ? ctx->d_planes : nullptr;
+  jobs.l[0].n_planes = slab.n_planes;
   jobs.l[0].aggregate = n_cells < n ? 1 : 0;
   k_hist_levels<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(cloud->d_xyz,
                                                                              (uint32_t)n, jobs);
@@ -874,7 +938,8 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   const uint32_t* d_stat = slab.on ? d_counts + sample_off_of(g) : d_counts;
   const uint64_t n_stat = slab.on ? sample_words_of(slab) : n_cells;
   k_cell_stats<<<grid_for(ctx, n_stat, kThreads * 4), kThreads, 0, ctx->stream>>>(
-      d_stat, n_stat, low_thr, ctx->d_scratch, ctx->h_scratch, seq);
+      d_stat, n_stat, low_thr, ctx->d_scratch, ctx->h_scratch, seq, ctx->d_planes,
+      planes ? slab.n_planes : 0);
   TC_LAUNCHED(ctx);
   TC_TRY(wait_host_flag(ctx, ctx->h_scratch + 15, seq));
   for (int j = 0; j < 7; ++j) stats[j] = ctx->h_scratch[8 + j];
@@ -972,9 +1037,15 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   float stat_scale = 1.0f;  // final cell / measured cell
   GridParams g = make_grid(mn, mx, cell, n, table_cap);
   cell = g.cell;
-  const Slab tslab = slab_of(g, rank, world, halo);  // (a slab build samples its statistics)
+  // (a slab build samples its statistics, and counts `margin` planes more on either side so the
+  //  boundaries can still move to balance the ranks' point counts)
+  const int margin = balance_margin(g.ymajor ? g.ny : g.nz, world);
+  const Slab tslab = slab_of(g, rank, world, halo + margin);
   st = trial_histogram(ctx, cloud, g, low_thr, tslab, &d_trial, stats);
   trace.mark("trial histogram+stats");
+  std::vector<uint32_t> plane_counts;
+  if (st == TC_OK && tslab.on && tslab.n_planes <= tc_context::kPlaneWords)
+    plane_counts.assign(ctx->h_scratch + 64, ctx->h_scratch + 64 + tslab.n_planes);
   if (st != TC_OK) {
     tc_ws_release_zeroed(ctx, 0, d_trial, false);
     delete ix;
@@ -1062,7 +1133,13 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
   // written or read: the search's ring cap (GridParams.flags bits 8..15) keeps it inside.
   Slab slab_off;
   slab_off.cell_hi = slab_off.own_cell_hi = cells_of(lg[0]);
-  const Slab sl = nl == 1 ? slab_of(lg[0], rank, world, halo) : slab_off;
+  Slab sl = nl == 1 ? slab_of(lg[0], rank, world, halo) : slab_off;
+  if (sl.on && primary_counted && !plane_counts.empty() && margin > 0) {
+    // point-balanced slabs (the grid is the trial's: its histogram covers them)
+    std::vector<int> bnd((size_t)world + 1);
+    balanced_boundaries(plane_counts.data(), sl.n_planes, n, world, margin, bnd.data());
+    sl = slab_planes(lg[0], world, bnd[rank], bnd[rank + 1], halo);
+  }
   const bool slab = sl.on;
   const uint64_t cell_lo = sl.cell_lo, cell_hi = sl.cell_hi, own_cell_lo = sl.own_cell_lo,
                  own_cell_hi = sl.own_cell_hi;
@@ -1130,6 +1207,12 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
       zero.n[1] = primary_counted ? 0 : tslab.on ? tslab.cell_hi - tslab.cell_lo + 1 : trial_words;
       zero.p[2] = d_trial + trial_sample_off;  // the statistics sample of a slab build
       zero.n[2] = sample_words_of(tslab);
+      if (primary_counted && tslab.on && slab) {  // counted for the margin, outside the final slab
+        zero.p[3] = d_trial + tslab.cell_lo;
+        zero.n[3] = cell_lo - tslab.cell_lo;
+        zero.p[4] = d_trial + cell_hi;
+        zero.n[4] = tslab.cell_hi - cell_hi;
+      }
       k_scatter_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, all, zero);
       ctx->launches++;
       trace.mark("launches: hist/scan/scatter");

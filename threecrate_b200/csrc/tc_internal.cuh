@@ -20,6 +20,11 @@ struct tc_context {
   uint64_t launches = 0;
   int sm_count = 148;
   // small device scratch (bbox / stats / flags) and its pinned host mirror
+  static constexpr int kPlaneWords = 4096;  // per-plane point counts of a slab build (words 64..)
+  static constexpr int kScratchWords = 64 + kPlaneWords;  // (host mirror: counts at 64..)
+  static constexpr int kPlaneStride = 32;   // device counters 128 B apart (one L2 line each: a
+                                            // thousand blocks add to every one of them)
+  uint32_t* d_planes = nullptr;    // kPlaneWords x kPlaneStride words, all zero between builds
   uint32_t* d_scratch = nullptr;   // 64 words
   uint32_t* h_scratch = nullptr;   // pinned + device-visible (UVA), 64 words: kernels publish small
                                    // results here and the host polls a sequence word
