@@ -75,8 +75,8 @@ __device__ __noinline__ uint32_t resolve_ties(const GridParams g, const uint32_t
 
 // Two-pass exact selection for one query (see k_knn2).  On success the sorted positions (into
 // `pts`) of the neighbours, ascending by (d2, index), are in s_b[0 .. n)[threadIdx.x] and n is
-// returned; -1 means "ties: use the exact chain kernel" (bit-equal d2 inside the list, or more
-// than `need` points at or below the K-th d2).
+// returned (bit-equal d2 are ordered by original index; more of them at the K-th d2 than the
+// member table holds are resolved by resolve_ties).
 //   pass 1  SelF: exact K-th squared distance tau (floats only, sorting networks)
 //   pass 2  re-scan the rows that can hold d2 <= tau, append each member's position to s_a
 //           (a 4-instruction append, so lanes that accept different candidates cost little)
@@ -276,10 +276,6 @@ k_knn2(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32
   const uint32_t qid = __float_as_uint(q.w);
   int level;
   const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, need, s_a, s_b, level);
-  if (n < 0) {
-    fb_list[atomicAdd(fb_count, 1u)] = qi;
-    return;
-  }
   knn_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, qid, k, drop_self, idx_out, dist_out,
            count_out);
 }
@@ -407,10 +403,6 @@ k_normals2(LevelSet ls, uint32_t q_begin, uint32_t q_end, uint32_t own_begin, ui
 #endif
   int level, R = 0;
   const int n = select_two_pass<L, X>(ls, q.x, q.y, q.z, k + 1, s_a, s_b, level, &R TC_DBG_ARG(dbg));
-  if (n < 0) {
-    fb_list[atomicAdd(fb_count, 1u)] = qi;
-    return;
-  }
   if (ls.halo && R > ls.halo) atomicAdd(ls.unsafe, 1u);  // slab index: may have missed points
   normals_emit(SortedPos{s_b, n, ls.pts[level], q.x, q.y, q.z}, q, qid, k, orient, vpx, vpy, vpz,
                route_out(ls, qid, out), (ls.g[0].flags & 128) != 0);
@@ -774,15 +766,20 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
     TC_LAUNCHED(ctx);
     return TC_OK;
   }
-  uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions that overflowed on ties
-  TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
-  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
+  const bool tile = (flags & 32) && !ix->sharded;
+  // the per-lane kernels resolve every query themselves (ties included, resolve_ties); only the
+  // staged-tile variant hands what it cannot prove to a list for the chain kernel
+  uint32_t* d_fb = nullptr;  // [0] = count, [1..] = query positions
+  if (tile) {
+    TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
+    TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  }
 #define TC_KNN2(LL, XX)                                                                       \
   k_knn2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(ls, d_queries_sorted, (uint32_t)q_begin,   \
                                                    (uint32_t)q_end, k, need, drop_self,       \
                                                    d_idx_out, d_dist_out, d_count_out, d_fb + 1, d_fb)
-  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
-  if ((flags & 32) && !ix->sharded) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+  if (tile) {  // staged-tile kernel (tc_tile.cu)
     uint32_t* d_stats = nullptr;
     ctx->stats_queries = nq;
     if (ctx->stats_on) {
@@ -800,6 +797,7 @@ int tci_knn_launch(tc_context* ctx, const tc_index* ix, const float4* d_queries_
       default: TC_KNN2(32, true); break;
     }
     TC_LAUNCHED(ctx);
+    return TC_OK;
   }
 #undef TC_KNN2
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
@@ -856,15 +854,18 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
     TC_LAUNCHED(ctx);
     return TC_OK;
   }
-  uint32_t* d_fb = nullptr;
-  TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
-  TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
+  const bool tile = (flags & 32) && !ix->sharded;
+  uint32_t* d_fb = nullptr;  // the staged-tile variant's list for the chain kernel (see tci_knn_launch)
+  if (tile) {
+    TC_TRY(tc_ws_get(ctx, 2, &d_fb, (uint64_t)nq + 1));
+    TC_CUDA(ctx, cudaMemsetAsync(d_fb, 0, sizeof(uint32_t), ctx->stream));
+  }
 #define TC_NORMALS2(LL, XX)                                                                  \
   k_normals2<LL, XX><<<grid, kBlock, 0, ctx->stream>>>(                                      \
       ls, (uint32_t)q_begin, (uint32_t)q_end, own_begin, own_end, k, orient, vp[0], vp[1],   \
       vp[2], d_out_aos, d_fb + 1, d_fb TC_DBG_ARG(g_tc_dbg))
-  // (a slab-sharded index keeps the per-lane kernel: its ring cap lives in grid_search)
-  if ((flags & 32) && !ix->sharded) {  // staged-tile kernel (tc_tile.cu); what it cannot prove goes to the list
+  if (tile) {  // staged-tile kernel (tc_tile.cu)
     uint32_t* d_stats = nullptr;
     ctx->stats_queries = nq;
     if (ctx->stats_on) {
@@ -882,6 +883,7 @@ int tci_normals_launch(tc_context* ctx, const tc_index* ix, uint32_t k, int orie
       default: TC_NORMALS2(32, true); break;
     }
     TC_LAUNCHED(ctx);
+    return TC_OK;
   }
 #undef TC_NORMALS2
   const dim3 fgrid(std::min<uint32_t>((nq + kBlock - 1) / kBlock, (uint32_t)ctx->sm_count));
