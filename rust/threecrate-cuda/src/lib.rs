@@ -66,7 +66,21 @@ extern "C" {
                                  min_neighbors: u32, out: *mut *mut TcCloud) -> c_int;
     fn tc_statistical_outlier_removal(ctx: *mut TcContext, c: *const TcCloud, k: u32, value: f32,
                                       mode: c_int, stats: *mut f32, out: *mut *mut TcCloud) -> c_int;
+    // multi-GPU (one process per GPU)
+    fn tc_comm_get_unique_id(ctx: *mut TcContext, id_out: *mut u8) -> c_int;
+    fn tc_comm_init_rank(ctx: *mut TcContext, id: *const u8, n_ranks: c_int, rank: c_int,
+                         out: *mut *mut TcComm) -> c_int;
+    fn tc_comm_destroy(comm: *mut TcComm);
+    fn tc_dist_chunk(n_total: u64, n_ranks: c_int, rank: c_int, lo: *mut u64, hi: *mut u64);
+    fn tc_comm_window_handle(comm: *mut TcComm, n_total: u64, handle_out: *mut u8) -> c_int;
+    fn tc_comm_window_open(comm: *mut TcComm, all_handles: *const u8) -> c_int;
+    fn tc_estimate_normals_distributed(ctx: *mut TcContext, comm: *mut TcComm, chunk_xyz: *const f32,
+                                       n_total: u64, k: u32, consistent: c_int,
+                                       viewpoint: *const f32, chunk_out: *mut f32) -> c_int;
 }
+#[repr(C)] pub struct TcComm { _p: [u8; 0] }
+pub const TC_COMM_ID_BYTES: usize = 128;
+pub const TC_IPC_HANDLE_BYTES: usize = 64;
 
 /// `IcpScaleLevel` (registration.rs:28-35) as it crosses the ABI; negative distance = None.
 #[repr(C)]
@@ -334,6 +348,60 @@ pub fn statistical_outlier_removal_with_threshold(points: &[Point3f], k: usize, 
     filter_with(points, |ctx, c, out| unsafe {
         tc_statistical_outlier_removal(ctx, c, k as u32, threshold, 2, ptr::null_mut(), out) })
 }
+
+/// One rank of a multi-GPU job (one process per GPU).  The 128-byte id (rank 0: `unique_id`) and
+/// the 64-byte window handles travel between the processes by whatever the host application has
+/// (MPI, a socket, a file): the library never opens a connection of its own.
+pub struct Comm { ctx: Context, comm: *mut TcComm, pub n_ranks: usize, pub rank: usize }
+
+impl Comm {
+    pub fn unique_id(ctx: &Context) -> Result<[u8; TC_COMM_ID_BYTES]> {
+        let mut id = [0u8; TC_COMM_ID_BYTES];
+        ctx.check(unsafe { tc_comm_get_unique_id(ctx.0, id.as_mut_ptr()) })?;
+        Ok(id)
+    }
+    pub fn new(device: i32, id: &[u8; TC_COMM_ID_BYTES], n_ranks: usize, rank: usize) -> Result<Self> {
+        let ctx = Context::new(device)?;
+        let mut p = ptr::null_mut();
+        ctx.check(unsafe { tc_comm_init_rank(ctx.0, id.as_ptr(), n_ranks as c_int, rank as c_int, &mut p) })?;
+        Ok(Self { ctx, comm: p, n_ranks, rank })
+    }
+    /// Rows `[lo, hi)` of an `n_total`-point cloud this rank passes in and gets back.
+    pub fn chunk(&self, n_total: usize) -> (usize, usize) {
+        let (mut lo, mut hi) = (0u64, 0u64);
+        unsafe { tc_dist_chunk(n_total as u64, self.n_ranks as c_int, self.rank as c_int, &mut lo, &mut hi) };
+        (lo as usize, hi as usize)
+    }
+    /// Step 1 of the window set-up (once per cloud size): this rank's handle, to be gathered.
+    pub fn window_handle(&self, n_total: usize) -> Result<[u8; TC_IPC_HANDLE_BYTES]> {
+        let mut h = [0u8; TC_IPC_HANDLE_BYTES];
+        self.ctx.check(unsafe { tc_comm_window_handle(self.comm, n_total as u64, h.as_mut_ptr()) })?;
+        Ok(h)
+    }
+    /// Step 2: the handles of ALL ranks, in rank order.
+    pub fn open_window(&self, handles: &[[u8; TC_IPC_HANDLE_BYTES]]) -> Result<()> {
+        assert_eq!(handles.len(), self.n_ranks);
+        let blob: Vec<u8> = handles.iter().flatten().copied().collect();
+        self.ctx.check(unsafe { tc_comm_window_open(self.comm, blob.as_ptr()) })
+    }
+    /// `estimate_normals` (normals.rs:238) of ONE cloud over all ranks: `chunk` = this rank's
+    /// rows `self.chunk(n_total)`; returns the `NormalPoint3f` of the same rows, bit-identical
+    /// to the single-GPU result.  Collective: every rank calls it.
+    pub fn estimate_normals(&self, chunk: &[Point3f], n_total: usize, k: usize) -> Result<Vec<NormalPoint3f>> {
+        let (lo, hi) = self.chunk(n_total);
+        if chunk.len() != hi - lo {
+            return Err(Error::InvalidData(format!("rank {} holds rows [{lo}, {hi})", self.rank)));
+        }
+        let mut out = vec![NormalPoint3f::default(); chunk.len()];
+        self.ctx.check(unsafe {
+            tc_estimate_normals_distributed(self.ctx.0, self.comm, chunk.as_ptr() as *const f32,
+                                            n_total as u64, k as u32, 1, ptr::null(),
+                                            out.as_mut_ptr() as *mut f32)
+        })?;
+        Ok(out)
+    }
+}
+impl Drop for Comm { fn drop(&mut self) { unsafe { tc_comm_destroy(self.comm) } } }
 
 #[allow(dead_code)]
 fn _unused(_: *mut c_void) {}

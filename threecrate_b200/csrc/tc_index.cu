@@ -210,11 +210,15 @@ __device__ __forceinline__ uint32_t point_cell(const GridParams& g, float x, flo
 
 // f(i, x, y, z) for every point, grid-stride.  A 16-byte aligned array is read four points (three
 // 128-bit loads) per thread and trip: a third of the load instructions, 48 bytes in flight.
+// (clouds below kVecPoints keep one point per thread: a LiDAR frame would otherwise fill fewer
+//  blocks than there are SMs; the launch sites size their grids with points_per_thread())
+constexpr uint32_t kVecPoints = 1u << 20;
+inline int points_per_thread(uint64_t n) { return n >= kVecPoints ? 4 : 1; }
 template <class F>
 __device__ __forceinline__ void for_each_point(const float* __restrict__ xyz, uint32_t n, F&& f) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   uint32_t done = 0;
-  if ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+  if (n >= kVecPoints && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
     const float4* v4 = reinterpret_cast<const float4*>(xyz);
     const uint32_t groups = n / 4;
     for (uint32_t gi = tid; gi < groups; gi += stride) {
@@ -931,8 +935,8 @@ int trial_histogram(tc_context* ctx, const tc_cloud* cloud, const GridParams& g,
   jobs.l[0].plane_counts = planes ? ctx->d_planes : nullptr;
   jobs.l[0].n_planes = slab.n_planes;
   jobs.l[0].aggregate = n_cells < n ? 1 : 0;
-  k_hist_levels<<<grid_for(ctx, n, kThreads * 4), kThreads, 0, ctx->stream>>>(cloud->d_xyz,
-                                                                             (uint32_t)n, jobs);
+  k_hist_levels<<<grid_for(ctx, n, kThreads * points_per_thread(n)), kThreads, 0, ctx->stream>>>(
+      cloud->d_xyz, (uint32_t)n, jobs);
   TC_LAUNCHED(ctx);
   const uint32_t seq = ++ctx->seq;
   const uint32_t* d_stat = slab.on ? d_counts + sample_off_of(g) : d_counts;
@@ -1191,7 +1195,7 @@ int tci_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, flo
       scan.out[l] = ix->d_arena + cs_off[l] + (slab ? cell_lo : 0);
       scan.len[l] = slab ? cell_hi - cell_lo : cells_of(lg[l]);
     }
-    const int grid = grid_for(ctx, n, kThreads * 4);  // (four points per thread and trip)
+    const int grid = grid_for(ctx, n, kThreads * points_per_thread(n));
     if (todo.n > 0) {
       k_hist_levels<<<grid, kThreads, 0, ctx->stream>>>(cloud->d_xyz, (uint32_t)n, todo);
       ctx->launches++;
