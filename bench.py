@@ -863,8 +863,9 @@ def bench_c5(E):
     # set compact): rank r holds the source points of the r-th of 8 slabs along y, so it touches
     # one eighth of the replicated target; N < 8 runs use the first N slabs
     slabs = max(8, E.world)
-    yr = (-1.0 + 2.0 * E.rank / slabs, -1.0 + 2.0 * (E.rank + 1) / slabs)
-    src, _ = terrain_dev(ns, 600 + E.rank, 0.005, False, yr)  # this rank's source shard
+    srank = int(os.environ.get("TC_C5_SLAB", E.rank))  # (debug: which slab a 1-GPU run takes)
+    yr = (-1.0 + 2.0 * srank / slabs, -1.0 + 2.0 * (srank + 1) / slabs)
+    src, _ = terrain_dev(ns, 600 + srank, 0.005, False, yr)  # this rank's source shard
     R = torch.tensor(synth.quat_to_matrix(Tinv[3:7]), dtype=torch.float32, device=dev)
     src = (src @ R.T + torch.tensor(Tinv[:3], dtype=torch.float32, device=dev)).contiguous()
     torch.cuda.synchronize()

@@ -1,6 +1,7 @@
 // tc_search.cuh — the exact grid search shared by the kNN / normals kernels (tc_search.cu) and
 // the ICP correspondence kernel (tc_icp.cu).  See tc_search.cu for the design notes.
 #pragma once
+#include <type_traits>
 #include "tc_internal.cuh"
 
 namespace tcs {
@@ -235,6 +236,7 @@ __device__ __forceinline__ float ring_bound(const GridParams& g, int R, int cx, 
 // 1-NN accumulator (ICP correspondences): best (d2, original index) key plus its sorted position.
 // `seeded`: key/pos were preset from a known candidate (the previous ICP iteration's match).
 struct Best1 {
+  static constexpr bool kOutside = true;  // ICP sources need not lie inside the target's grid
   uint64_t key;
   uint32_t pos;
   bool seeded = false;
@@ -282,6 +284,20 @@ struct Best1 {
 
 // Conservative lower bound (squared) on the distance from the query to any point in row
 // (y, z): per axis the gap, in cell units, between the query and the nearest face of that row.
+// Accumulators whose queries may lie outside the grid (ICP sources against a target's index)
+// declare `static constexpr bool kOutside = true`: the query's OWN row then gets the distance
+// from the query to the grid face as its gap, not zero.  A source point 3 m above the target's
+// bounding box otherwise treats every row of the top plane within 3 m horizontally as a
+// candidate row, although none of it can be nearer than 3 m.
+template <class A, class = void>
+struct acc_outside : std::false_type {};
+template <class A>
+struct acc_outside<A, std::void_t<decltype(A::kOutside)>> : std::bool_constant<A::kOutside> {};
+template <bool OUTSIDE>
+__device__ __forceinline__ float own_row_gap(float f) {
+  // f = fractional cell coordinate relative to the CLAMPED cell: < 0 below the grid, > 1 above
+  return OUTSIDE ? fmaxf(0.0f, fmaxf(f - 1.0f, -f)) : 0.0f;
+}
 __device__ __forceinline__ float row_gap(int d, float f) {
   // d = row coordinate - query cell coordinate along the axis; f = fractional cell coordinate
   return d == 0 ? 0.0f : (d < 0 ? (f + (float)(-d - 1)) : ((float)d - f));
@@ -328,8 +344,11 @@ __device__ __forceinline__ int grid_search(const GridParams& g, const float4* __
         float byz = 0.0f;
         const bool prune = (flags & 2) && tk.full();
         if (prune) {
-          const float by = axis_bound(row_gap(dy, fy), g.cell, my);
-          const float bz = axis_bound(row_gap(dz, fz), g.cell, mz);
+          constexpr bool kOut = acc_outside<Acc>::value;
+          const float by =
+              axis_bound(dy == 0 ? own_row_gap<kOut>(fy) : row_gap(dy, fy), g.cell, my);
+          const float bz =
+              axis_bound(dz == 0 ? own_row_gap<kOut>(fz) : row_gap(dz, fz), g.cell, mz);
           byz = by * by + bz * bz;
           if (byz * 0.99999f > tk.kth()) continue;  // every point of the row is farther
         }
@@ -427,6 +446,14 @@ __device__ __forceinline__ int level_search(const LevelSet& ls, float qx, float 
   for (; start_level < 0 && l < ls.n - 1; ++l) {
     const GridParams& g = ls.g[l];
     if (by_block) {
+      if (acc_outside<Acc>::value) {
+        // a query more than a cell outside the grid: the block around its CLAMPED cell says
+        // nothing about its neighbourhood - leave the fine levels to queries that are inside
+        const float ux = (qx - g.ox) * g.inv, uy = (qy - g.oy) * g.inv, uz = (qz - g.oz) * g.inv;
+        if (ux < -1.0f || uy < -1.0f || uz < -1.0f || ux > (float)g.nx + 1.0f ||
+            uy > (float)g.ny + 1.0f || uz > (float)g.nz + 1.0f)
+          continue;
+      }
       if (block_population(g, ls.cs[l], qx, qy, qz) >= need) break;
       continue;
     }
