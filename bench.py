@@ -420,8 +420,8 @@ def main():
     scaled = bool(tr and prof_pts)
     roofline = {
         "bound": "hbm",
-        "kernel": "k_normals2<16,+1> (fused two-pass kNN + covariance + eigen + orientation; the "
-                  "timed call includes the tie-list chain launch)",
+        "kernel": "k_normals2<16,+1> (fused two-pass kNN + covariance + eigen + orientation; ties at "
+                  "rank k resolved inside the kernel)",
         "achieved": achieved, "peak": E.peak_gbs, "unit": "GB/s", "frac": achieved / E.peak_gbs,
         "peak_kind": f"of {E.peak_kind}",
         "traffic": (tr * q_launch / prof_pts) if scaled else None,
