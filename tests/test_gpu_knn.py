@@ -218,3 +218,30 @@ def test_degenerate_geometry(orc, case):
     assert np.all(np.isfinite(nrm)) and np.allclose(np.linalg.norm(nrm[:, 3:], axis=1), 1.0, atol=1e-5)
     vox = tc.voxel_grid_filter(pts, 0.5)
     assert np.array_equal(vox.view(np.uint32), orc.voxel_grid_filter(pts, 0.5).view(np.uint32))
+
+
+@pytest.mark.parametrize("k", [15, 16, 17, 31, 32])
+@pytest.mark.parametrize("cloud", ["lattice", "duplicates", "lattice3d"])
+def test_ties_wider_than_the_member_table_are_resolved_in_place(orc, cloud, k):
+    """k + 1 == table width (k = 16 / 32 and their neighbours): ANY bit-equal d2 straddling rank k
+    overflows the member table of the two-pass selection, which then collects the members in place
+    (resolve_ties: strictly-below first, then the points at the k-th distance in ascending index).
+    Lattices tie at every rank, duplicated points tie at distance zero; the rows must equal the
+    canonical (d2, index) order of the brute force bit for bit."""
+    rng = np.random.default_rng(12)
+    pts = {"lattice": synth.grid_plane(40, 0.125),
+           "duplicates": np.repeat(rng.uniform(-1, 1, (600, 3)).astype(np.float32), 5, axis=0),
+           "lattice3d": np.stack(np.meshgrid(*[np.arange(12, dtype=np.float32) * 0.25] * 3,
+                                             indexing="ij"), -1).reshape(-1, 3)}[cloud]
+    pts = np.ascontiguousarray(pts[rng.permutation(len(pts))])
+    idx, dist, cnt = tc.KdTree(pts, k_hint=k).knn(pts, k)
+    bi, bd2 = _brute(orc, pts, pts, k)
+    assert np.array_equal(idx.astype(np.uint64), bi)
+    assert np.array_equal(dist, np.sqrt(bd2))
+    sidx, sdist, scnt = tc.k_nearest_neighbors(pts, k)      # kNN(k+1), own index dropped
+    bi1, _ = _brute(orc, pts, pts, k + 1)
+    for i in range(0, len(pts), 37):
+        assert sidx[i].tolist() == [j for j in bi1[i].tolist() if j != i][:k]
+    # the normals kernel runs the same selection: it must terminate and produce unit normals
+    nrm = tc.estimate_normals(pts, k)[:, 3:]
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
