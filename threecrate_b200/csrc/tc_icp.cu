@@ -278,6 +278,7 @@ k_icp_correspond(LevelSet ls, const float4* __restrict__ tgt_nrm,
               }
             }
           }
+          best.far = true;
           level_search(ls, s.x, s.y, s.z, 1u, best, level, have ? level : -1);
           if (have && best.full()) covered = sqrtf(best.kth());
         } else {

@@ -253,10 +253,43 @@ struct Best1 {
   }
   __device__ __forceinline__ bool full() const { return key != kEmpty; }
   __device__ __forceinline__ float kth() const { return __uint_as_float((uint32_t)(key >> 32)); }
+  // far mode (set by the caller for queries many cells from the surface, where a search scans a
+  // thousand candidates and improves its best a handful of times): a candidate strictly farther
+  // than the best costs one compare and one min; everything else takes the exact key path
+  bool far = false;
   __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t lo, uint32_t hi,
                                        float qx, float qy, float qz, int) {
     if (lo >= hi) return;
     const uint32_t last = hi - 1;
+    if (far) {
+      float bd = kth();  // NaN while empty: `d2 > bd` is then false and the key path decides
+#pragma unroll 1
+      for (uint32_t base = lo; base < hi; base += 4) {
+        float4 c[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) c[t] = __ldg(&pts[min(base + t, last)]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float d2 = dist2_exact(c[t].x, c[t].y, c[t].z, qx, qy, qz);
+          if (base + t > last) continue;
+          if (d2 > bd) {
+            second = fminf(second, d2);
+            continue;
+          }
+          const uint64_t k2 =
+              ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c[t].w);
+          if (k2 < key) {
+            second = fminf(second, kth());
+            key = k2;
+            pos = base + t;
+            bd = d2;
+          } else if (k2 != key) {
+            second = fminf(second, d2);
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll 1
     for (uint32_t base = lo; base < hi; base += 4) {
       // four independent loads in flight (clamped: a repeated last candidate cannot win twice)

@@ -14,7 +14,7 @@ import threecrate_b200 as tc  # noqa: E402
 from fixtures import synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["c2", "c4", "c3", "knn", "gicp", "filters"])
+ap.add_argument("what", choices=["c2", "c4", "c3", "c5far", "knn", "gicp", "filters"])
 ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--k", type=int, default=30)
@@ -56,6 +56,32 @@ elif a.what == "c3":
         index = tc.GridIndex(tcloud, k_hint=1)
         r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, a.iters, None, -1.0)
         print(index.info(), r.translation)
+        index.free()
+elif a.what == "c5far":
+    # the far regime of C5 at a size ncu can replay: C5's point density (250 / m^2), a source slab
+    # lifted ~2.4-3 m off the surface at the cloud edge (roll about x), first iteration unseeded
+    n = a.n or 4_000_000
+    H = 316.0 * (n / 1e8) ** 0.5
+    rng = np.random.default_rng(5)
+    xy = rng.uniform(-H, H, (n, 2)).astype(np.float32)
+    z = (0.5 * np.sin(0.3 * xy[:, 0]) * np.cos(0.2 * xy[:, 1]) + rng.normal(0, 0.005, n)).astype(np.float32)
+    tgt = np.column_stack([xy, z]).astype(np.float32)
+    gx = 0.15 * np.cos(0.3 * xy[:, 0]) * np.cos(0.2 * xy[:, 1])
+    gy = -0.1 * np.sin(0.3 * xy[:, 0]) * np.sin(0.2 * xy[:, 1])
+    nrm = np.column_stack([-gx, -gy, np.ones(n)])
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    m = n // 8
+    sxy = np.column_stack([rng.uniform(-H, H, m), rng.uniform(0.75 * H, H, m)]).astype(np.float32)
+    sz = (0.5 * np.sin(0.3 * sxy[:, 0]) * np.cos(0.2 * sxy[:, 1]) + 3.0 * sxy[:, 1] / H).astype(np.float32)
+    src = np.column_stack([sxy, sz]).astype(np.float32)
+    tcloud, scloud = tc.DeviceCloud(tgt, ctx), tc.DeviceCloud(src, ctx)
+    d_nrm = ctx.alloc(n * 12)
+    ctx.to_device(d_nrm, nrm)
+    for _ in range(a.reps):
+        index = tc.GridIndex(tcloud, k_hint=1)
+        ctx.timer_start()
+        r = tc.icp_point_to_plane_device(scloud, index, d_nrm, tc.IDENTITY, a.iters, None, -1.0)
+        print(index.info()["dims"], index.info()["n_levels"], r.translation, f"{ctx.timer_stop():.3f} ms")
         index.free()
 elif a.what == "gicp":
     n = a.n or 200_000
