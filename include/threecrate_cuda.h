@@ -133,11 +133,13 @@ int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint, floa
                    tc_index** out);
 void tc_index_free(tc_index* index);
 /* Multi-GPU normals (queries sharded, one process per GPU, no data-path collective): every rank
- * calls this on ITS copy of the same cloud.  The ranks agree on one grid (bbox, cell size and
- * level decisions come from the whole cloud), cut it into `world` slabs of whole cell planes along
- * its longest axis, and rank `rank` sorts only the points of its slab plus a halo of a few planes -
- * the counting-sort scatter, the cell-range scan and the shared-memory-sized tables shrink by
- * ~1/world.  tc_estimate_normals_device on such an index computes exactly the rank's own rows
+ * calls this on ITS copy of the same cloud.  The ranks agree on one grid without talking (bbox from
+ * the whole cloud; cell size and level decisions from the statistics of every 8th cell plane,
+ * which every rank histograms alike), cut it into `world` slabs of whole cell planes along its
+ * longest axis - the boundaries placed so that the slabs hold equal numbers of POINTS (per-plane
+ * counts of the whole cloud, identical on every rank) - and rank `rank` counts, scans and sorts only
+ * the cells of its slab plus a halo of a few planes: the histogram atomics, the cell-range scan and
+ * the counting-sort scatter shrink by ~1/world.  tc_estimate_normals_device on such an index computes exactly the rank's own rows
  * (pass shard range [0, UINT64_MAX)); should a query ever need points beyond the halo the call
  * transparently finishes on a complete index, so results never depend on the sharding.  Clouds that
  * need several grid resolutions, or have fewer planes than ranks, get a complete index and the
