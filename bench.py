@@ -339,10 +339,12 @@ def main():
     total_ms = E.max_over_ranks(float(np.sum(ms_step)))
     value = n * args.steps / (total_ms * 1e-3)
     per_rank_ms = [float(np.sum(ms_step)) / args.steps]
+    per_rank_split = [(float(np.mean(ms_index)), float(np.mean(ms_kernel)))]
     if world > 1:
         gathered = [None] * world
-        dist.all_gather_object(gathered, per_rank_ms[0])
-        per_rank_ms = [float(x) for x in gathered]
+        dist.all_gather_object(gathered, (per_rank_ms[0],) + per_rank_split[0])
+        per_rank_ms = [float(x[0]) for x in gathered]
+        per_rank_split = [(float(x[1]), float(x[2])) for x in gathered]
     info = tc.GridIndex(cloud, k_hint=K_HEAD)
     grid_info = info.info()
     info.free()
@@ -462,6 +464,8 @@ def main():
                    "l2": "flushed (256 MiB write) before every step; working set > L2",
                    "timed": "CUDA events on the library stream, summed over steps, max over ranks",
                    "ms_per_step_by_rank": [round(x, 5) for x in per_rank_ms],
+                   "ms_build_and_kernel_by_rank": [[round(b, 4), round(k, 4)]
+                                                   for b, k in per_rank_split],
                    "grid": {"cell_size": grid_info["cell_size"], "dims": list(grid_info["dims"]),
                             "levels": grid_info["n_levels"]},
                    "cpu_affinity": (f"NVML-local CPUs of the rank's GPU ({len(E.affinity)} cores)"
