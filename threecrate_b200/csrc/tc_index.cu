@@ -961,6 +961,14 @@ extern "C" void tc_debug_set_max_levels(int n) {
 
 int g_tc_shard_halo = 4;  // planes built beyond the rank's own slab on either side
 extern "C" void tc_debug_set_shard_halo(int planes) { g_tc_shard_halo = planes < 1 ? 1 : planes; }
+// (host logic of the slab build, exported for the CPU tests: the boundaries every rank derives
+//  from the per-plane point counts; bnd has world + 1 entries)
+extern "C" void tc_debug_balanced_boundaries(const uint32_t* plane_counts, int n_planes, int world,
+                                             int* bnd) {
+  uint64_t n = 0;
+  for (int p = 0; p < n_planes; ++p) n += plane_counts[p];
+  balanced_boundaries(plane_counts, n_planes, n, world, balance_margin(n_planes, world), bnd);
+}
 
 extern "C" int tc_index_build(tc_context* ctx, const tc_cloud* cloud, uint32_t k_hint,
                               float cell_size, tc_index** out) {
