@@ -300,8 +300,10 @@ int tc_comm_allreduce_f64(tc_comm* comm, double* d_buf, uint64_t count);
  * chunk, pulls the other chunks out of the peers' windows over NVLink, builds the slab-sharded
  * index (tc_index_build_sharded), and its normals kernel writes every row straight into the
  * window of the rank that owns it; two stream-ordered peer barriers, no collective call.
- * Set-up (once per cloud size): every rank calls tc_comm_window_handle, the host gathers the
- * handles of all ranks (rank order) and passes the concatenation to tc_comm_window_open.
+ * Set-up (once per cloud size, collective): every rank calls tc_comm_window_handle, the host
+ * gathers the handles of all ranks (rank order) and passes the concatenation to
+ * tc_comm_window_open.  A rank's previous window stays allocated until its next
+ * tc_comm_window_open, when no peer can still have it mapped.
  * kNN mode only (radius-mode normals: shard tc_estimate_normals_device by sorted range). */
 void tc_dist_chunk(uint64_t n_total, int n_ranks, int rank, uint64_t* lo, uint64_t* hi);
 int tc_comm_window_handle(tc_comm* comm, uint64_t n_total, void* handle_out /* TC_IPC_HANDLE_BYTES */);

@@ -30,6 +30,7 @@ struct tc_comm {
   char* win_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t win_n = 0, win_chunk = 0, win_out_off = 0, win_bytes = 0;
   bool win_open = false;
+  char* win_retired = nullptr;       // the previous window: freed once every peer has let go of it
   unsigned long long bar_epoch = 0;  // barriers passed so far (identical on every rank)
   uint32_t* d_err = nullptr;         // a barrier that timed out sets this
 };
@@ -177,13 +178,23 @@ static uint64_t dist_chunk_len(uint64_t n, int n_ranks) {
   return std::max<uint64_t>(4, (((n + w - 1) / w) + 3) & ~(uint64_t)3);
 }
 
-static void window_close(tc_comm* comm) {
+// Lets go of the peers' windows and retires the own one.  An exported allocation must not be
+// freed while a peer still has it mapped: the own window is only freed by the NEXT
+// tc_comm_window_open (the host has gathered every rank's new handle by then, so every rank has
+// been through here and closed its mapping) or at tc_comm_destroy.
+static void window_close(tc_comm* comm, bool free_now) {
   if (comm->win_open)
     for (int r = 0; r < comm->n_ranks; ++r)
       if (r != comm->rank && comm->win_peer[r]) cudaIpcCloseMemHandle(comm->win_peer[r]);
   for (int r = 0; r < 8; ++r) comm->win_peer[r] = nullptr;
   comm->win_open = false;
-  if (comm->win) cudaFree(comm->win);
+  if (comm->win_retired) cudaFree(comm->win_retired);  // (two generations old: nobody maps it)
+  comm->win_retired = nullptr;
+  if (free_now) {
+    if (comm->win) cudaFree(comm->win);
+  } else {
+    comm->win_retired = comm->win;
+  }
   comm->win = nullptr;
   comm->win_n = 0;
 }
@@ -196,7 +207,7 @@ extern "C" int tc_comm_window_handle(tc_comm* comm, uint64_t n_points, void* han
     return tc_fail(ctx, TC_INVALID_DATA, "window: 0 < n_points < 2^32-1");
   TC_CUDA(ctx, cudaSetDevice(ctx->device));
   TC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  window_close(comm);
+  window_close(comm, false);
   comm->win_n = n_points;
   comm->win_chunk = dist_chunk_len(n_points, comm->n_ranks);
   // (the cloud region is sized for whole chunks so that every rank's chunk copy stays inside)
@@ -221,6 +232,10 @@ extern "C" int tc_comm_window_open(tc_comm* comm, const void* all_handles) {
   tc_context* ctx = comm->ctx;
   if (!comm->win) return tc_fail(ctx, TC_INVALID_DATA, "call tc_comm_window_handle first");
   TC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (comm->win_retired) {  // every rank has created its new window, i.e. closed the old mappings
+    cudaFree(comm->win_retired);
+    comm->win_retired = nullptr;
+  }
   for (int r = 0; r < comm->n_ranks; ++r) {
     if (r == comm->rank) {
       comm->win_peer[r] = comm->win;
@@ -381,7 +396,7 @@ extern "C" int tc_estimate_normals_distributed(tc_context* ctx, tc_comm* comm,
 
 extern "C" void tc_comm_destroy(tc_comm* comm) {
   if (!comm) return;
-  window_close(comm);
+  window_close(comm, true);
   if (comm->d_err) cudaFree(comm->d_err);
   if (comm->peers_open)
     for (int r = 0; r < comm->n_ranks; ++r)
