@@ -392,12 +392,13 @@ impl Comm {
         if chunk.len() != hi - lo {
             return Err(Error::InvalidData(format!("rank {} holds rows [{lo}, {hi})", self.rank)));
         }
-        let mut out = vec![NormalPoint3f::default(); chunk.len()];
+        let mut out: Vec<NormalPoint3f> = Vec::with_capacity(chunk.len());
         self.ctx.check(unsafe {
             tc_estimate_normals_distributed(self.ctx.0, self.comm, chunk.as_ptr() as *const f32,
                                             n_total as u64, k as u32, 1, ptr::null(),
                                             out.as_mut_ptr() as *mut f32)
         })?;
+        unsafe { out.set_len(chunk.len()) };  // (every row written by the call: repr(C) 6 x f32)
         Ok(out)
     }
 }
