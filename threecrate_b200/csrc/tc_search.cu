@@ -261,8 +261,10 @@ k_knn(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_
 }
 
 // Two-pass kernel: pass 1 finds the exact K-th squared distance with the float selection list,
-// pass 2 re-scans and collects the (d2, index) keys with d2 <= tau into shared memory, which a
-// single u64 bitonic sort then orders.  More than L members (ties) -> fallback list.
+// pass 2 re-scans and collects the positions of the points with d2 <= tau into shared memory and
+// ranks them.  More members than the table holds (ties at rank k) are resolved in place
+// (resolve_ties); fb_list / fb_count are no longer written by this kernel (the staged-tile
+// variant shares the launch signature and still hands its unproven queries to the list).
 template <int L, bool X>
 __global__ void __launch_bounds__(kBlock)
 k_knn2(LevelSet ls, const float4* __restrict__ queries, uint32_t q_begin, uint32_t q_end,
