@@ -78,3 +78,51 @@ def test_own_row_gap_is_what_makes_the_top_plane_prunable():
     assert _axis_bound(_row_gap(np.array([0]), f, False), cell, mag)[0] == 0
     b = _axis_bound(_row_gap(np.array([0]), f, True), cell, mag)[0]
     assert 14.9 * 0.2 < b <= 15.0 * 0.2
+
+
+def _d2(p, q):
+    """dist2_exact: (dx*dx + dy*dy) + dz*dz in f32, no FMA."""
+    d = (p - q).astype(F)
+    return ((d[..., 0] * d[..., 0]).astype(F) + (d[..., 1] * d[..., 1]).astype(F)).astype(F) + \
+        (d[..., 2] * d[..., 2]).astype(F)
+
+
+def test_icp_keep_rule_never_keeps_a_match_that_a_search_would_change():
+    """tc_icp.cu keeps last iteration's match without a search when
+         (d + |s - q_full|) (1 + 2e-5) + 3e-7 |s|_1 < a (1 - 2e-5),
+    a = distance from q_full (the position at the last full search) to the nearest OTHER point.
+    Whenever the rule fires, the brute-force nearest neighbour at s under the reference's order
+    (smallest f32 d2, strict <: ties go to the lower index) must be that same point - including
+    near-ties constructed to sit on the edge of the rule."""
+    rng = np.random.default_rng(7)
+    fired = 0
+    for trial in range(300):
+        n = 64
+        scale = F(10.0 ** rng.uniform(-1, 3))
+        tgt = (rng.normal(size=(n, 3)) * scale).astype(F)
+        q_full = (tgt[rng.integers(0, n, 256)] + (rng.normal(size=(256, 3)) * scale * 0.2)).astype(F)
+        d2_full = _d2(tgt[None, :, :], q_full[:, None, :])                  # [256, n]
+        order = np.lexsort((np.arange(n)[None, :].repeat(256, 0), d2_full), axis=1)
+        match = order[:, 0]
+        a = np.sqrt(np.take_along_axis(d2_full, order[:, 1:2], 1)[:, 0]).astype(F)  # nearest other
+        # move the query: random steps, plus steps aimed at the runner-up sized to graze the rule
+        step = (rng.normal(size=(256, 3)) * scale * 0.05).astype(F)
+        runner = tgt[order[:, 1]]
+        aim = runner - q_full
+        aim /= np.maximum(np.linalg.norm(aim, axis=1, keepdims=True), 1e-20)
+        d0 = np.sqrt(d2_full[np.arange(256), match])
+        graze = ((a - d0) * 0.5 * rng.uniform(0.9, 1.1, 256))[:, None] * aim
+        step[::2] = graze[::2].astype(F)
+        s = (q_full + step).astype(F)
+        d2_now = _d2(tgt[None, :, :], s[:, None, :])
+        d = np.sqrt(d2_now[np.arange(256), match]).astype(F)
+        m = (s - q_full).astype(F)
+        moved = np.sqrt(((m[:, 0] * m[:, 0]).astype(F) + (m[:, 1] * m[:, 1]).astype(F)).astype(F) +
+                        (m[:, 2] * m[:, 2]).astype(F)).astype(F)
+        lhs = ((d + moved).astype(F) * F(1.00002)).astype(F) + \
+            (F(3e-7) * np.abs(s).sum(1).astype(F)).astype(F)
+        keep = (a > 0) & (lhs < (a * F(0.99998)).astype(F))
+        brute = np.lexsort((np.arange(n)[None, :].repeat(256, 0), d2_now), axis=1)[:, 0]
+        assert np.array_equal(brute[keep], match[keep])
+        fired += int(keep.sum())
+    assert fired > 10_000   # the rule does fire (about half of the trials)
