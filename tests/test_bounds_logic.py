@@ -126,3 +126,33 @@ def test_icp_keep_rule_never_keeps_a_match_that_a_search_would_change():
         assert np.array_equal(brute[keep], match[keep])
         fired += int(keep.sum())
     assert fired > 10_000   # the rule does fire (about half of the trials)
+
+
+def test_box_query_cells_cover_every_point_within_the_radius():
+    """box_cells (tc_search.cuh): the cells [cell(q - r'), cell(q + r')] per axis, r' = sqrt(r2)
+    inflated by 1e-5 relative + 1e-6 (|q|_1 + cell), hold every indexed point within distance
+    sqrt(r2) of the query - the exactness of seeded ICP searches, radius queries and the radius
+    outlier count rests on it.  Points are placed at |p - q| <= r on the axis, many exactly at r."""
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        n = int(rng.integers(1, 3000))
+        cell = F(10.0 ** rng.uniform(-3, 1))
+        inv = F(1.0) / cell
+        o = F(rng.uniform(-500, 500))
+        m = 5000
+        q = (o + rng.uniform(-5, n + 5, m).astype(F) * cell).astype(F)
+        other = (rng.uniform(-100, 100, (m, 2))).astype(F)            # the query's other two coordinates
+        r = (10.0 ** rng.uniform(-4, 1, m)).astype(F) * cell
+        r2 = (r * r).astype(F)
+        frac = rng.uniform(-1, 1, m)
+        frac[: m // 3] = np.sign(frac[: m // 3])                       # exactly at the radius
+        p = (q + (frac * r.astype(np.float64)).astype(F)).astype(F)
+        # only points whose f32 squared distance really is <= r2 count as "within"
+        within = ((p - q).astype(F) * (p - q).astype(F)).astype(F) <= r2
+        rr = (np.sqrt(r2).astype(F) * F(1.00001)).astype(F) + \
+            (F(1e-6) * (np.abs(q) + np.abs(other).sum(1).astype(F) + cell).astype(F)).astype(F) + F(1e-30)
+        lo, _ = _cell_coord((q - rr).astype(F), o, inv, n)
+        hi, _ = _cell_coord((q + rr).astype(F), o, inv, n)
+        cp, _ = _cell_coord(p, o, inv, n)
+        ok = (cp >= lo) & (cp <= hi)
+        assert np.all(ok[within]), (n, float(cell))
